@@ -1,0 +1,620 @@
+// lce_b200.cu -- implementation of the C-ABI CUDA layer declared in
+// include/lce_b200.h. Host-side logic restates what the reference's op shell
+// does around its kernels (LCE = /root/reference/larq_compute_engine):
+//   shape inference          LCE/tflite/kernels/bconv2d.cc:169-248,
+//                            tensorflow/lite/kernels/padding.h:32-82
+//   output-transform fold    LCE/tflite/kernels/bconv2d.cc:353-389 (in double, on the host)
+// and launches the kernels of lce_b200_kernels.cuh. There is no CPU compute path.
+#include <atomic>
+#include <climits>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "lce_b200.h"
+#include "lce_b200_kernels.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<uint64_t> g_launches{0};
+
+int fail(const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return 1;
+}
+
+#define CUDA_OK(expr)                                                            \
+  do {                                                                           \
+    cudaError_t e__ = (expr);                                                    \
+    if (e__ != cudaSuccess)                                                      \
+      return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+  } while (0)
+
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+
+int launch_check(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+
+int grid_for(long long work_items, int per_block, int max_blocks = 148 * 16) {
+  long long b = (work_items + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+// tensorflow/lite/kernels/padding.h:42-60
+int out_size(int padding, int image, int filter, int stride, int dil) {
+  const int eff = (filter - 1) * dil + 1;
+  if (stride == 0) return 0;
+  if (padding == LCE_PADDING_SAME) return (image + stride - 1) / stride;
+  if (padding == LCE_PADDING_VALID) return (image + stride - eff) / stride;
+  return 0;
+}
+// tensorflow/lite/kernels/padding.h:32-40
+int pad_before(int stride, int dil, int in, int filter, int out) {
+  const int eff = (filter - 1) * dil + 1;
+  int total = (out - 1) * stride + eff - in;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+
+bool is_device_ptr(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+// Copy `bytes` from a host-or-device pointer into fresh device memory of
+// `alloc_bytes` (zero padded).
+int to_device(const void* src, size_t bytes, size_t alloc_bytes, void** dst) {
+  CUDA_OK(cudaMalloc(dst, alloc_bytes));
+  CUDA_OK(cudaMemset(*dst, 0, alloc_bytes));
+  if (bytes)
+    CUDA_OK(cudaMemcpy(*dst, src, bytes,
+                       is_device_ptr(src) ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice));
+  return 0;
+}
+int to_host(const void* src, size_t bytes, void* dst) {
+  CUDA_OK(cudaMemcpy(dst, src, bytes,
+                     is_device_ptr(src) ? cudaMemcpyDeviceToHost : cudaMemcpyHostToHost));
+  return 0;
+}
+
+// The part of a plan that the implicit-GEMM kernel needs, shared by LceBconv2d
+// and the plain BGEMM.
+struct GemmCore {
+  int V = 1;            // words per smem vector (largest of 4,2,1 dividing Cw_pg)
+  int Cw_pg = 0, taps = 1, Kv = 0, Kc_v = 0, n_chunks = 1;
+  int cout = 0, cout_pg = 0, groups = 1, tiles_per_group = 1;
+  int out_type = LCE_OUT_FLOAT;
+  int clamp_min = 0, clamp_max = 0;
+  int32_t* wt = nullptr;        // tiled weights
+  float* mul = nullptr;         // folded, padded
+  float* bias = nullptr;
+  int32_t* thr = nullptr;
+  int32_t* tap_popc = nullptr;  // zero-padding correction table
+  size_t smem_bytes = 0;
+
+  void release() {
+    cudaFree(wt); cudaFree(mul); cudaFree(bias); cudaFree(thr); cudaFree(tap_popc);
+    wt = nullptr; mul = bias = nullptr; thr = tap_popc = nullptr;
+  }
+};
+
+template <int V, int OUT>
+int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_OK(cudaFuncSetAttribute(lce::bconv_kernel<V, OUT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (lce::kBM + lce::kBN) * lce::kMaxChunkWords * 4));
+    attr_set = true;
+  }
+  lce::bconv_kernel<V, OUT><<<grid, lce::kThreads, smem, s>>>(p);
+  return launch_check("bconv_kernel");
+}
+template <int V>
+int launch_conv_v(int out_type, const lce::ConvKParams& p, dim3 grid, size_t smem,
+                  cudaStream_t s) {
+  switch (out_type) {
+    case LCE_OUT_FLOAT: return launch_conv_vo<V, LCE_OUT_FLOAT>(p, grid, smem, s);
+    case LCE_OUT_INT8: return launch_conv_vo<V, LCE_OUT_INT8>(p, grid, smem, s);
+    case LCE_OUT_BITPACKED: return launch_conv_vo<V, LCE_OUT_BITPACKED>(p, grid, smem, s);
+    case LCE_OUT_RAW_ACC: return launch_conv_vo<V, LCE_OUT_RAW_ACC>(p, grid, smem, s);
+  }
+  return fail("unsupported output type %d", out_type);
+}
+int launch_conv(const GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
+  if (p.M <= 0) return 0;  // empty batch: nothing to do
+  const long long m_tiles = (p.M + lce::kBM - 1) / lce::kBM;
+  if (m_tiles > INT_MAX) return fail("too many output pixels");
+  dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(c.groups * c.tiles_per_group));
+  switch (c.V) {
+    case 4: return launch_conv_v<4>(c.out_type, p, grid, c.smem_bytes, s);
+    case 2: return launch_conv_v<2>(c.out_type, p, grid, c.smem_bytes, s);
+    default: return launch_conv_v<1>(c.out_type, p, grid, c.smem_bytes, s);
+  }
+}
+
+// Build the tiled weights (+ optional tap popcounts) from an OHWI-packed filter
+// [cout][taps][Cw_pg] that may live on the host or the device.
+int build_core_weights(GemmCore* c, const int32_t* filter, bool want_tap_popc) {
+  const size_t filter_words = static_cast<size_t>(c->cout) * c->taps * c->Cw_pg;
+  int32_t* d_filter = nullptr;
+  const bool on_dev = is_device_ptr(filter);
+  if (!on_dev) {
+    void* tmp = nullptr;
+    if (to_device(filter, filter_words * 4, filter_words * 4 + 16, &tmp)) return 1;
+    d_filter = static_cast<int32_t*>(tmp);
+  } else {
+    d_filter = const_cast<int32_t*>(filter);
+  }
+  c->V = (c->Cw_pg % 4 == 0) ? 4 : (c->Cw_pg % 2 == 0) ? 2 : 1;
+  const int CwV = c->Cw_pg / c->V;
+  c->Kv = c->taps * CwV;
+  const int max_kc_v = lce::kMaxChunkWords / c->V;
+  c->n_chunks = cdiv(c->Kv, max_kc_v);
+  c->Kc_v = cdiv(c->Kv, c->n_chunks);
+  c->smem_bytes = static_cast<size_t>(c->Kc_v) * (lce::kBM + lce::kBN) * c->V * 4;
+  c->tiles_per_group = cdiv(c->cout_pg, lce::kBN);
+  const long long total = static_cast<long long>(c->groups) * c->tiles_per_group * c->Kv *
+                          lce::kBN * c->V;
+  CUDA_OK(cudaMalloc(&c->wt, total * 4));
+  lce::tile_weights_kernel<<<grid_for(total, 256, 1 << 20), 256>>>(
+      d_filter, c->wt, c->cout_pg, c->tiles_per_group, c->taps, c->Cw_pg, c->V, c->Kv, total);
+  if (launch_check("tile_weights_kernel")) return 1;
+  if (want_tap_popc) {
+    const size_t n = static_cast<size_t>(c->cout + lce::kBN) * c->taps;
+    CUDA_OK(cudaMalloc(&c->tap_popc, n * 4));
+    CUDA_OK(cudaMemset(c->tap_popc, 0, n * 4));
+    lce::tap_popc_kernel<<<cdiv(c->cout * c->taps, 256), 256>>>(d_filter, c->tap_popc, c->cout,
+                                                                c->taps, c->Cw_pg);
+    if (launch_check("tap_popc_kernel")) return 1;
+  }
+  CUDA_OK(cudaDeviceSynchronize());
+  if (!on_dev) cudaFree(d_filter);
+  return 0;
+}
+
+bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace
+
+// ------------------------------------------------------------------------- //
+struct lce_b200_bconv2d {
+  lce_bconv2d_desc d;
+  int out_h = 0, out_w = 0, pad_h = 0, pad_w = 0;
+  GemmCore core;
+  int32_t* packed_scratch = nullptr;  // run_f32: packed activations
+  size_t packed_scratch_words = 0;
+  void* h2d_in = nullptr;             // run_host staging
+  void* d2h_out = nullptr;
+  size_t h2d_bytes = 0, d2h_bytes = 0;
+};
+
+struct lce_b200_bgemm {
+  GemmCore core;
+  int N = 0, Kw = 0;
+};
+
+extern "C" {
+
+int lce_b200_abi_version(void) { return LCE_B200_ABI_VERSION; }
+const char* lce_b200_last_error(void) { return g_err.c_str(); }
+uint64_t lce_b200_launch_count(void) { return g_launches.load(); }
+
+int lce_b200_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+// ------------------------------ LceQuantize ------------------------------ //
+int lce_b200_quantize(int in_type, const void* in_dev, int64_t rows, int64_t cols,
+                      int32_t zero_point, int32_t* out_dev, void* stream) {
+  if (rows < 0 || cols < 0) return fail("quantize: negative shape");
+  if (rows == 0 || cols == 0) return 0;
+  if (cols > INT_MAX) return fail("quantize: last dimension too large");
+  cudaStream_t s = as_stream(stream);
+  const int cw = static_cast<int>((cols + 31) / 32);
+  const long long n_words = rows * cw;
+  switch (in_type) {
+    case LCE_T_FLOAT:
+      if (cols % 32 == 0 && aligned16(in_dev)) {
+        lce::pack_f32_flat_kernel<<<grid_for(n_words * 4, 256), 256, 0, s>>>(
+            static_cast<const float4*>(in_dev), out_dev, n_words);
+        return launch_check("pack_f32_flat_kernel");
+      }
+      lce::pack_generic_kernel<float><<<grid_for(n_words * 32, 256), 256, 0, s>>>(
+          static_cast<const float*>(in_dev), out_dev, rows, static_cast<int>(cols), cw, 0);
+      return launch_check("pack_generic_kernel<float>");
+    case LCE_T_INT8:
+      lce::pack_generic_kernel<int8_t><<<grid_for(n_words * 32, 256), 256, 0, s>>>(
+          static_cast<const int8_t*>(in_dev), out_dev, rows, static_cast<int>(cols), cw,
+          zero_point);
+      return launch_check("pack_generic_kernel<int8>");
+    case LCE_T_BOOL:
+      lce::pack_generic_kernel<uint8_t><<<grid_for(n_words * 32, 256), 256, 0, s>>>(
+          static_cast<const uint8_t*>(in_dev), out_dev, rows, static_cast<int>(cols), cw, 1);
+      return launch_check("pack_generic_kernel<bool>");
+  }
+  return fail("quantize: unsupported input type %d", in_type);
+}
+
+// ----------------------------- LceDequantize ----------------------------- //
+int lce_b200_dequantize(int out_type, const int32_t* in_dev, int64_t rows, int64_t cols,
+                        float scale, int32_t zero_point, void* out_dev, void* stream) {
+  if (rows < 0 || cols < 0) return fail("dequantize: negative shape");
+  if (rows == 0 || cols == 0) return 0;
+  if (cols > INT_MAX) return fail("dequantize: last dimension too large");
+  cudaStream_t s = as_stream(stream);
+  const int cw = static_cast<int>((cols + 31) / 32);
+  const int grid = grid_for(rows * cols, 256);
+  switch (out_type) {
+    case LCE_T_FLOAT:
+      lce::unpack_kernel<float><<<grid, 256, 0, s>>>(in_dev, static_cast<float*>(out_dev), rows,
+                                                     static_cast<int>(cols), cw, 1.0f, -1.0f);
+      return launch_check("unpack_kernel<float>");
+    case LCE_T_INT8: {
+      // quantization.cc:130-138
+      const int offset = static_cast<int>(std::round(1.0f / scale));
+      const int8_t zero_bit = static_cast<int8_t>(std::min(127, zero_point + offset));
+      const int8_t one_bit = static_cast<int8_t>(std::max(-128, zero_point - offset));
+      lce::unpack_kernel<int8_t><<<grid, 256, 0, s>>>(in_dev, static_cast<int8_t*>(out_dev), rows,
+                                                      static_cast<int>(cols), cw, zero_bit,
+                                                      one_bit);
+      return launch_check("unpack_kernel<int8>");
+    }
+    case LCE_T_BOOL:
+      lce::unpack_kernel<uint8_t><<<grid, 256, 0, s>>>(in_dev, static_cast<uint8_t*>(out_dev),
+                                                       rows, static_cast<int>(cols), cw,
+                                                       uint8_t(1), uint8_t(0));
+      return launch_check("unpack_kernel<bool>");
+  }
+  return fail("dequantize: unsupported output type %d", out_type);
+}
+
+// ----------------------------- LceBMaxPool2d ----------------------------- //
+int lce_b200_bmaxpool_out_shape(const lce_bmaxpool_desc* d, int* out_h, int* out_w) {
+  // bmaxpool.cc:51-54
+  if (!d->stride_h || !d->stride_w || !d->filter_h || !d->filter_w)
+    return fail("bmaxpool: strides and filter sizes must be non-zero");
+  if (d->padding != LCE_PADDING_SAME && d->padding != LCE_PADDING_VALID)
+    return fail("bmaxpool: unknown padding %d", d->padding);
+  *out_h = out_size(d->padding, d->in_h, d->filter_h, d->stride_h, 1);
+  *out_w = out_size(d->padding, d->in_w, d->filter_w, d->stride_w, 1);
+  return 0;
+}
+
+int lce_b200_bmaxpool(const lce_bmaxpool_desc* d, const int32_t* in_dev, int32_t* out_dev,
+                      void* stream) {
+  int oh, ow;
+  if (lce_b200_bmaxpool_out_shape(d, &oh, &ow)) return 1;
+  const long long n = static_cast<long long>(d->batch) * oh * ow * d->channels_packed;
+  if (n <= 0) return 0;
+  const int ph = pad_before(d->stride_h, 1, d->in_h, d->filter_h, oh);
+  const int pw = pad_before(d->stride_w, 1, d->in_w, d->filter_w, ow);
+  lce::bmaxpool_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+      in_dev, out_dev, d->batch, d->in_h, d->in_w, d->channels_packed, oh, ow, d->filter_h,
+      d->filter_w, d->stride_h, d->stride_w, ph, pw);
+  return launch_check("bmaxpool_kernel");
+}
+
+// ------------------------------- LceBconv2d ------------------------------ //
+int lce_b200_bconv2d_out_shape(const lce_bconv2d_desc* d, int* out_h, int* out_w, int* pad_h,
+                               int* pad_w) {
+  if (d->pad_value != 0 && d->pad_value != 1)
+    return fail("Attribute pad_values must be 0 or 1.");  // bconv2d.cc:113-116
+  if (d->padding != LCE_PADDING_SAME && d->padding != LCE_PADDING_VALID)
+    return fail("bconv2d: unknown padding %d", d->padding);
+  if (d->groups < 1 || d->channels_in < 1 || d->channels_out < 1 || d->filter_h < 1 ||
+      d->filter_w < 1 || d->stride_h < 1 || d->stride_w < 1 || d->dilation_h < 1 ||
+      d->dilation_w < 1)
+    return fail("bconv2d: non-positive parameter");
+  // bconv2d.cc:169-186
+  if (d->channels_in % d->groups != 0)
+    return fail("bconv2d: channels_in %d not divisible by groups %d", d->channels_in, d->groups);
+  if (d->groups > 1 && (d->channels_in / d->groups) % 32 != 0)
+    return fail("bconv2d: grouped convolutions need channels_in/groups %% 32 == 0");
+  if (d->channels_out % d->groups != 0)
+    return fail("bconv2d: channels_out %d not divisible by groups %d", d->channels_out,
+                d->groups);
+  *out_h = out_size(d->padding, d->in_h, d->filter_h, d->stride_h, d->dilation_h);
+  *out_w = out_size(d->padding, d->in_w, d->filter_w, d->stride_w, d->dilation_w);
+  *pad_h = pad_before(d->stride_h, d->dilation_h, d->in_h, d->filter_h, *out_h);
+  *pad_w = pad_before(d->stride_w, d->dilation_w, d->in_w, d->filter_w, *out_w);
+  if (*out_h < 0) *out_h = 0;
+  if (*out_w < 0) *out_w = 0;
+  return 0;
+}
+
+int lce_b200_bconv2d_create(const lce_bconv2d_desc* d, const int32_t* filter,
+                            const float* post_mul, const float* post_bias,
+                            const int32_t* thresholds, lce_b200_bconv2d** out_plan) {
+  *out_plan = nullptr;
+  if (lce_b200_device_count() < 1) return fail("no CUDA device: this library has no CPU path");
+  int oh, ow, ph, pw;
+  if (lce_b200_bconv2d_out_shape(d, &oh, &ow, &ph, &pw)) return 1;
+  if (d->out_type != LCE_OUT_FLOAT && d->out_type != LCE_OUT_INT8 &&
+      d->out_type != LCE_OUT_BITPACKED)
+    return fail("Supported output types are int8, int32, and float32.");  // bconv2d.cc:158-162
+  const bool zero_pad = d->padding == LCE_PADDING_SAME && d->pad_value == 0;
+  if (zero_pad && d->channels_in % 2 != 0)  // bconv2d.cc:188-200, reference-kernel rule
+    return fail("Zero-padding is only supported by the reference kernel with an even number of "
+                "input channels, or when using float output with no fused activation function.");
+  if (d->out_type == LCE_OUT_BITPACKED) {
+    if (!thresholds) return fail("bconv2d: bitpacked output needs the thresholds input");
+  } else if (!post_mul || !post_bias) {
+    return fail("bconv2d: float/int8 output needs post_activation_multiplier and bias");
+  }
+  if (!filter) return fail("bconv2d: filter is null");
+
+  auto* plan = new lce_b200_bconv2d();
+  plan->d = *d;
+  plan->out_h = oh; plan->out_w = ow; plan->pad_h = ph; plan->pad_w = pw;
+  GemmCore& c = plan->core;
+  c.groups = d->groups;
+  c.cout = d->channels_out;
+  c.cout_pg = d->channels_out / d->groups;
+  c.Cw_pg = cdiv(d->channels_in / d->groups, 32);
+  c.taps = d->filter_h * d->filter_w;
+  c.out_type = d->out_type;
+  int rc = build_core_weights(&c, filter, zero_pad);
+
+  const size_t padded = static_cast<size_t>(c.cout) + lce::kBN;
+  if (!rc && d->out_type != LCE_OUT_BITPACKED) {
+    // OneTimeSetup (bconv2d.cc:353-389): fold in double on the host.
+    std::vector<float> pm(c.cout), pb(c.cout), fm(padded, 0.f), fb(padded, 0.f);
+    rc = to_host(post_mul, c.cout * sizeof(float), pm.data()) ||
+         to_host(post_bias, c.cout * sizeof(float), pb.data());
+    const int32_t backtransform_add = d->filter_h * d->filter_w * (d->channels_in / d->groups);
+    const double scale = d->out_type == LCE_OUT_INT8 ? static_cast<double>(d->out_scale) : 1.0;
+    const double zp = d->out_type == LCE_OUT_INT8 ? static_cast<double>(d->out_zero_point) : 0.0;
+    for (int i = 0; i < c.cout; ++i) {
+      const double m = pm[i], b = pb[i];
+      fm[i] = static_cast<float>(-1 * m / scale);
+      fb[i] = static_cast<float>((b + static_cast<double>(backtransform_add) * m) / scale + zp);
+    }
+    int32_t nmin, nmax;  // CalculateActivationRange<int32>, kernel_util.h:285-300
+    switch (d->activation) {
+      case LCE_ACT_RELU: nmin = 0; nmax = INT32_MAX; break;
+      case LCE_ACT_RELU6: nmin = 0; nmax = 6; break;
+      case LCE_ACT_RELU_N1_TO_1: nmin = -1; nmax = 1; break;
+      default: nmin = INT32_MIN; nmax = INT32_MAX; break;
+    }
+    nmin = std::max(nmin, -backtransform_add);
+    nmax = std::min(nmax, backtransform_add);
+    c.clamp_min = -nmax + backtransform_add;
+    c.clamp_max = -nmin + backtransform_add;
+    void *dm = nullptr, *db = nullptr;
+    rc = rc || to_device(fm.data(), padded * 4, padded * 4, &dm) ||
+         to_device(fb.data(), padded * 4, padded * 4, &db);
+    c.mul = static_cast<float*>(dm);
+    c.bias = static_cast<float*>(db);
+  } else if (!rc) {
+    void* dt = nullptr;
+    rc = to_device(thresholds, c.cout * 4, padded * 4, &dt);
+    c.thr = static_cast<int32_t*>(dt);
+  }
+  if (rc) {
+    c.release();
+    delete plan;
+    return 1;
+  }
+  *out_plan = plan;
+  return 0;
+}
+
+int lce_b200_bconv2d_set_input_shape(lce_b200_bconv2d* plan, int batch, int in_h, int in_w) {
+  lce_bconv2d_desc d = plan->d;
+  d.batch = batch; d.in_h = in_h; d.in_w = in_w;
+  if (batch < 0 || in_h < 1 || in_w < 1) return fail("bconv2d: bad input shape");
+  int oh, ow, ph, pw;
+  if (lce_b200_bconv2d_out_shape(&d, &oh, &ow, &ph, &pw)) return 1;
+  plan->d = d;
+  plan->out_h = oh; plan->out_w = ow; plan->pad_h = ph; plan->pad_w = pw;
+  return 0;
+}
+
+int lce_b200_bconv2d_get_desc(const lce_b200_bconv2d* plan, lce_bconv2d_desc* d, int* out_h,
+                              int* out_w) {
+  *d = plan->d;
+  *out_h = plan->out_h;
+  *out_w = plan->out_w;
+  return 0;
+}
+
+static size_t bconv_out_bytes(const lce_b200_bconv2d* plan) {
+  const size_t px = static_cast<size_t>(plan->d.batch) * plan->out_h * plan->out_w;
+  switch (plan->d.out_type) {
+    case LCE_OUT_BITPACKED: return px * cdiv(plan->d.channels_out, 32) * 4;
+    case LCE_OUT_INT8: return px * plan->d.channels_out;
+    default: return px * plan->d.channels_out * 4;
+  }
+}
+
+int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev, void* out_dev,
+                         void* stream) {
+  const lce_bconv2d_desc& d = plan->d;
+  const GemmCore& c = plan->core;
+  cudaStream_t s = as_stream(stream);
+  lce::ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = in_dev; p.wt = c.wt; p.out = out_dev;
+  p.mul = c.mul; p.bias = c.bias; p.thr = c.thr; p.tap_popc = c.tap_popc;
+  p.M = static_cast<long long>(d.batch) * plan->out_h * plan->out_w;
+  p.H = d.in_h; p.W = d.in_w;
+  p.Cw_total = cdiv(d.channels_in, 32);
+  p.Cw_pg = c.Cw_pg; p.CwV = c.Cw_pg / c.V;
+  p.KH = d.filter_h; p.KW = d.filter_w;
+  p.sh = d.stride_h; p.sw = d.stride_w; p.dh = d.dilation_h; p.dw = d.dilation_w;
+  p.ph = plan->pad_h; p.pw = plan->pad_w; p.OH = plan->out_h; p.OW = plan->out_w;
+  p.cout = c.cout; p.cout_pg = c.cout_pg; p.tiles_per_group = c.tiles_per_group;
+  p.Kv = c.Kv; p.Kc_v = c.Kc_v; p.n_chunks = c.n_chunks;
+  p.clamp_min = c.clamp_min; p.clamp_max = c.clamp_max;
+  p.cw_out = cdiv(c.cout, 32);
+  p.zp_half = (d.channels_in / d.groups) / 2;
+  if (d.out_type == LCE_OUT_INT8)
+    p.vec_store = (c.cout % 8 == 0 && c.cout_pg % 8 == 0 &&
+                   (reinterpret_cast<uintptr_t>(out_dev) & 7u) == 0);
+  else
+    p.vec_store = (c.cout % 4 == 0 && c.cout_pg % 4 == 0 && aligned16(out_dev));
+  p.bp_fast = (c.groups == 1 || c.cout_pg % 32 == 0);
+  if (p.M == 0) return 0;
+  // The 4V-byte cp.async gathers need 4V-byte aligned pixels.
+  if ((reinterpret_cast<uintptr_t>(in_dev) & (4u * c.V - 1)) != 0)
+    return fail("bconv2d: input pointer must be %d-byte aligned", 4 * c.V);
+  if (d.out_type == LCE_OUT_BITPACKED && !p.bp_fast)
+    CUDA_OK(cudaMemsetAsync(out_dev, 0, bconv_out_bytes(plan), s));
+  return launch_conv(c, p, s);
+}
+
+int lce_b200_bconv2d_run_f32(lce_b200_bconv2d* plan, const float* in_dev, void* out_dev,
+                             void* stream) {
+  const lce_bconv2d_desc& d = plan->d;
+  const int cw = cdiv(d.channels_in, 32);
+  const size_t rows = static_cast<size_t>(d.batch) * d.in_h * d.in_w;
+  const size_t words = rows * cw;
+  if (words > plan->packed_scratch_words) {
+    cudaFree(plan->packed_scratch);
+    plan->packed_scratch = nullptr;
+    plan->packed_scratch_words = 0;
+    CUDA_OK(cudaMalloc(&plan->packed_scratch, words * 4 + 16));
+    plan->packed_scratch_words = words;
+  }
+  if (lce_b200_quantize(LCE_T_FLOAT, in_dev, static_cast<int64_t>(rows), d.channels_in, 0,
+                        plan->packed_scratch, stream))
+    return 1;
+  return lce_b200_bconv2d_run(plan, plan->packed_scratch, out_dev, stream);
+}
+
+int lce_b200_bconv2d_run_host(lce_b200_bconv2d* plan, const int32_t* in_host, void* out_host) {
+  const lce_bconv2d_desc& d = plan->d;
+  const size_t in_bytes =
+      static_cast<size_t>(d.batch) * d.in_h * d.in_w * cdiv(d.channels_in, 32) * 4;
+  const size_t out_bytes = bconv_out_bytes(plan);
+  if (in_bytes > plan->h2d_bytes) {
+    cudaFree(plan->h2d_in);
+    plan->h2d_in = nullptr; plan->h2d_bytes = 0;
+    CUDA_OK(cudaMalloc(&plan->h2d_in, in_bytes + 16));
+    plan->h2d_bytes = in_bytes;
+  }
+  if (out_bytes > plan->d2h_bytes) {
+    cudaFree(plan->d2h_out);
+    plan->d2h_out = nullptr; plan->d2h_bytes = 0;
+    CUDA_OK(cudaMalloc(&plan->d2h_out, out_bytes + 16));
+    plan->d2h_bytes = out_bytes;
+  }
+  if (in_bytes) CUDA_OK(cudaMemcpyAsync(plan->h2d_in, in_host, in_bytes, cudaMemcpyHostToDevice, 0));
+  if (lce_b200_bconv2d_run(plan, static_cast<const int32_t*>(plan->h2d_in), plan->d2h_out,
+                           nullptr))
+    return 1;
+  if (out_bytes)
+    CUDA_OK(cudaMemcpyAsync(out_host, plan->d2h_out, out_bytes, cudaMemcpyDeviceToHost, 0));
+  CUDA_OK(cudaStreamSynchronize(0));
+  return 0;
+}
+
+void lce_b200_bconv2d_destroy(lce_b200_bconv2d* plan) {
+  if (!plan) return;
+  plan->core.release();
+  cudaFree(plan->packed_scratch);
+  cudaFree(plan->h2d_in);
+  cudaFree(plan->d2h_out);
+  delete plan;
+}
+
+// --------------------------------- BGEMM --------------------------------- //
+int lce_b200_bgemm_create(int N, int Kw, const int32_t* W, const lce_bgemm_epilogue* ep,
+                          lce_b200_bgemm** out_plan) {
+  *out_plan = nullptr;
+  if (lce_b200_device_count() < 1) return fail("no CUDA device: this library has no CPU path");
+  if (N < 1 || Kw < 1 || !W || !ep) return fail("bgemm: bad arguments");
+  if (ep->out_type < LCE_OUT_FLOAT || ep->out_type > LCE_OUT_RAW_ACC)
+    return fail("bgemm: unsupported output type %d", ep->out_type);
+  auto* plan = new lce_b200_bgemm();
+  plan->N = N; plan->Kw = Kw;
+  GemmCore& c = plan->core;
+  c.groups = 1; c.cout = N; c.cout_pg = N; c.Cw_pg = Kw; c.taps = 1;
+  c.out_type = ep->out_type;
+  c.clamp_min = ep->clamp_min; c.clamp_max = ep->clamp_max;
+  int rc = build_core_weights(&c, W, false);
+  const size_t padded = static_cast<size_t>(N) + lce::kBN;
+  if (!rc && (ep->out_type == LCE_OUT_FLOAT || ep->out_type == LCE_OUT_INT8)) {
+    if (!ep->multiplier || !ep->bias) rc = fail("bgemm: multiplier/bias missing");
+    void *dm = nullptr, *db = nullptr;
+    rc = rc || to_device(ep->multiplier, N * 4, padded * 4, &dm) ||
+         to_device(ep->bias, N * 4, padded * 4, &db);
+    c.mul = static_cast<float*>(dm);
+    c.bias = static_cast<float*>(db);
+  } else if (!rc && ep->out_type == LCE_OUT_BITPACKED) {
+    if (!ep->thresholds) rc = fail("bgemm: thresholds missing");
+    void* dt = nullptr;
+    rc = rc || to_device(ep->thresholds, N * 4, padded * 4, &dt);
+    c.thr = static_cast<int32_t*>(dt);
+  }
+  if (rc) {
+    c.release();
+    delete plan;
+    return 1;
+  }
+  *out_plan = plan;
+  return 0;
+}
+
+int lce_b200_bgemm_run(lce_b200_bgemm* plan, int64_t M, const int32_t* A_dev, void* out_dev,
+                       void* stream) {
+  const GemmCore& c = plan->core;
+  if (M < 0) return fail("bgemm: negative M");
+  if (M == 0) return 0;
+  if (M > INT_MAX) return fail("bgemm: M too large");
+  lce::ConvKParams p;
+  memset(&p, 0, sizeof(p));
+  p.in = A_dev; p.wt = c.wt; p.out = out_dev;
+  p.mul = c.mul; p.bias = c.bias; p.thr = c.thr; p.tap_popc = nullptr;
+  p.M = M;
+  p.H = 1; p.W = static_cast<int>(M);
+  p.Cw_total = plan->Kw; p.Cw_pg = plan->Kw; p.CwV = plan->Kw / c.V;
+  p.KH = p.KW = 1; p.sh = p.sw = p.dh = p.dw = 1; p.ph = p.pw = 0;
+  p.OH = 1; p.OW = static_cast<int>(M);
+  p.cout = c.cout; p.cout_pg = c.cout_pg; p.tiles_per_group = c.tiles_per_group;
+  p.Kv = c.Kv; p.Kc_v = c.Kc_v; p.n_chunks = c.n_chunks;
+  p.clamp_min = c.clamp_min; p.clamp_max = c.clamp_max;
+  p.cw_out = cdiv(c.cout, 32);
+  if (c.out_type == LCE_OUT_INT8)
+    p.vec_store = (c.cout % 8 == 0 && (reinterpret_cast<uintptr_t>(out_dev) & 7u) == 0);
+  else
+    p.vec_store = (c.cout % 4 == 0 && aligned16(out_dev));
+  p.bp_fast = 1;
+  if ((reinterpret_cast<uintptr_t>(A_dev) & (4u * c.V - 1)) != 0)
+    return fail("bgemm: A must be %d-byte aligned", 4 * c.V);
+  return launch_conv(c, p, as_stream(stream));
+}
+
+void lce_b200_bgemm_destroy(lce_b200_bgemm* plan) {
+  if (!plan) return;
+  plan->core.release();
+  delete plan;
+}
+
+}  // extern "C"

@@ -1,0 +1,523 @@
+// lce_b200_kernels.cuh -- hand-written sm_100a kernels for the LCE binary-conv
+// hot path. No tensor cores by design (BASELINE.json north_star: sm_100a has no
+// b1 MMA); the inner product is XOR + POPC on the integer pipes, operands staged
+// in shared memory as 128-bit vectors, weights brought in by the TMA bulk-copy
+// engine (cp.async.bulk -> UBLKCP) onto an mbarrier, activations gathered with
+// zero-filling cp.async (LDGSTS), and the OutputTransform fused into the epilogue.
+//
+// Reference semantics (LCE = /root/reference/larq_compute_engine):
+//   K1 bsign_pack      LCE/core/bitpacking/bitpack.h:114-308
+//   K2/K3 bconv/bgemm  LCE/core/bconv2d/reference.h:35-148, optimized_bgemm.h:64-178,
+//                      LCE/core/bgemm/kernels.h:22-134, output_transform.h:94-168
+//   K4 bmaxpool        LCE/core/bmaxpool.h:24-88
+//   K5 unpack          LCE/core/bitpacking/bitpack.h:312-346
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "lce_b200_types.h"
+
+namespace lce {
+
+// ------------------------------------------------------------------------- //
+// Tile configuration of the binary implicit-GEMM kernel.
+//   CTA tile  BM x BN = 128 output pixels x 64 output channels, 256 threads.
+//   Warp tile 16 x 64 (lanes: 4 along M x 8 along N), thread tile 4 x 8.
+// ------------------------------------------------------------------------- //
+constexpr int kBM = 128;
+constexpr int kBN = 64;
+constexpr int kThreads = 256;
+constexpr int kTM = 4;
+constexpr int kTN = 8;
+// Upper bound on K words staged per chunk: (BM+BN)*Kc*4 B = 96 KiB -> 2 CTAs/SM.
+constexpr int kMaxChunkWords = 128;
+
+struct ConvKParams {
+  const int32_t* in;        // bitpacked NHWC activations
+  const int32_t* wt;        // tiled weights [n_tiles][Kv][BN][V]
+  void* out;
+  const float* mul;         // folded multiplier (padded to cout + BN)
+  const float* bias;        // folded bias
+  const int32_t* thr;       // thresholds
+  const int32_t* tap_popc;  // [cout + BN][taps] popcounts, zero-padding correction; or nullptr
+  long long M;              // batch * out_h * out_w
+  int H, W, Cw_total, Cw_pg, CwV;
+  int KH, KW, sh, sw, dh, dw, ph, pw, OH, OW;
+  int cout, cout_pg, tiles_per_group;
+  int Kv, Kc_v, n_chunks;
+  int clamp_min, clamp_max;
+  int cw_out;        // words per output pixel (bitpacked output)
+  int zp_half;       // channels_in_per_group / 2 (zero-padding correction)
+  int vec_store;     // output rows are 16B-aligned for this thread's 8 channels
+  int bp_fast;       // bitpacked output: tiles start on a 32-channel boundary
+};
+
+// --------------------------- PTX helpers ---------------------------------- //
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count)
+               : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+// TMA bulk copy global -> shared (1-D, no tensor map). SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes,
+                                         uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+      ::"r"(smem_u32(dst_smem)),
+      "l"(static_cast<uint64_t>(__cvta_generic_to_global(src_gmem))), "r"(bytes),
+      "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "LCE_WAIT:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra LCE_DONE;\n"
+      "bra LCE_WAIT;\n"
+      "LCE_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst_smem)),
+               "l"(src), "n"(BYTES), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <int V> struct VecT;
+template <> struct VecT<1> { using T = uint32_t; };
+template <> struct VecT<2> { using T = uint2; };
+template <> struct VecT<4> { using T = uint4; };
+
+__device__ __forceinline__ int xor_popc(uint32_t a, uint32_t b) { return __popc(a ^ b); }
+__device__ __forceinline__ int xor_popc(const uint2& a, const uint2& b) {
+  return __popc(a.x ^ b.x) + __popc(a.y ^ b.y);
+}
+__device__ __forceinline__ int xor_popc(const uint4& a, const uint4& b) {
+  return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
+}
+
+// OutputTransform<float>::Run, output_transform.h:100-106: shift, int32 clamp,
+// int->float, then an UNFUSED multiply and add (two roundings).
+__device__ __forceinline__ float transform_float(int acc, int cmin, int cmax, float mul,
+                                                 float bias) {
+  int x = acc << 1;
+  x = max(min(x, cmax), cmin);
+  return __fadd_rn(__fmul_rn(static_cast<float>(x), mul), bias);
+}
+// core::round (std::round, ties away) + x86 cvttss2si semantics + saturate,
+// types.h:50-94, output_transform.h:132-143.
+__device__ __forceinline__ int round_saturate_i8(float y) {
+  const float r = roundf(y);
+  int q = (r >= -2147483648.0f && r < 2147483648.0f) ? static_cast<int>(r) : INT32_MIN;
+  return max(-128, min(127, q));
+}
+
+// ------------------------------------------------------------------------- //
+// K2/K3: binary implicit-GEMM convolution (a plain BGEMM is the 1x1 case).
+//   acc[m][n] = sum_k popc(A[m][k] ^ W[n][k]),  k = (tap, channel word)
+// One CTA computes a 128-pixel x 64-channel tile; K is staged chunk by chunk:
+// weights by one bulk TMA copy from the pre-tiled layout, activation patches by
+// zero-filling 4V-byte cp.async (out-of-bounds taps read as 0 bits = +1, the
+// reference's one-padding: reference.h:106, optimized_bgemm.h:30-31).
+// ------------------------------------------------------------------------- //
+template <int V, int OUT>
+__global__ void __launch_bounds__(kThreads, 2) bconv_kernel(const ConvKParams p) {
+  using Vec = typename VecT<V>::T;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Vec* A_s = reinterpret_cast<Vec*>(smem_raw);     // [Kc_v][BM]
+  Vec* W_s = A_s + static_cast<size_t>(p.Kc_v) * kBM;  // [Kc_v][BN]
+  __shared__ __align__(8) uint64_t wbar;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tn = lane & 7, tm = lane >> 3;
+  const int nt = blockIdx.y;
+  const int g = nt / p.tiles_per_group;
+  const int tg = nt - g * p.tiles_per_group;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kBM;
+
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // ---- per-thread gather state: pixel `lp`, every second k-vector ---------
+  const int lp = tid & (kBM - 1);
+  const int half = tid >> 7;
+  const long long gm = m0 + lp;
+  const bool pix_valid = gm < p.M;
+  int iy0 = 0, ix0 = 0;
+  const int32_t* img = p.in;
+  if (pix_valid) {
+    const int ohw = p.OH * p.OW;
+    const long long b = gm / ohw;
+    const int r = static_cast<int>(gm - b * ohw);
+    const int oy = r / p.OW;
+    const int ox = r - oy * p.OW;
+    iy0 = oy * p.sh - p.ph;
+    ix0 = ox * p.sw - p.pw;
+    img = p.in + b * p.H * static_cast<long long>(p.W) * p.Cw_total +
+          static_cast<long long>(g) * p.Cw_pg;
+  }
+
+  int acc[kTM][kTN];
+#pragma unroll
+  for (int i = 0; i < kTM; ++i)
+#pragma unroll
+    for (int j = 0; j < kTN; ++j) acc[i][j] = 0;
+
+  uint32_t phase = 0;
+  for (int ch = 0; ch < p.n_chunks; ++ch) {
+    const int kv0 = ch * p.Kc_v;
+    const int kv1 = min(kv0 + p.Kc_v, p.Kv);
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(kv1 - kv0) * kBN * V * 4u;
+      mbar_arrive_expect_tx(&wbar, bytes);
+      bulk_g2s(W_s, p.wt + (static_cast<size_t>(nt) * p.Kv + kv0) * kBN * V, bytes, &wbar);
+    }
+    {
+      int kv = kv0 + half;
+      int tap = kv / p.CwV;
+      int cv = kv - tap * p.CwV;
+      int fy = tap / p.KW;
+      int fx = tap - fy * p.KW;
+      for (; kv < kv1; kv += 2) {
+        const int iy = iy0 + fy * p.dh;
+        const int ix = ix0 + fx * p.dw;
+        const bool inside = pix_valid && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
+                            static_cast<unsigned>(ix) < static_cast<unsigned>(p.W);
+        const int32_t* src =
+            inside ? img + (static_cast<long long>(iy) * p.W + ix) * p.Cw_total + cv * V : p.in;
+        cp_async_zfill<V * 4>(&A_s[static_cast<size_t>(kv - kv0) * kBM + lp], src,
+                              inside ? V * 4 : 0);
+        cv += 2;
+        while (cv >= p.CwV) {
+          cv -= p.CwV;
+          if (++fx == p.KW) {
+            fx = 0;
+            ++fy;
+          }
+        }
+      }
+    }
+    cp_async_wait_all();
+    mbar_wait(&wbar, phase);
+    phase ^= 1u;
+    __syncthreads();
+
+    const Vec* a_ptr = A_s + warp * 16 + tm;
+    const Vec* w_ptr = W_s + tn;
+    const int nkv = kv1 - kv0;
+#pragma unroll(V == 4 ? 1 : (V == 2 ? 2 : 4))
+    for (int kv = 0; kv < nkv; ++kv) {
+      Vec a[kTM], w[kTN];
+#pragma unroll
+      for (int i = 0; i < kTM; ++i) a[i] = a_ptr[kv * kBM + i * 4];
+#pragma unroll
+      for (int j = 0; j < kTN; ++j) w[j] = w_ptr[kv * kBN + j * 8];
+#pragma unroll
+      for (int i = 0; i < kTM; ++i)
+#pragma unroll
+        for (int j = 0; j < kTN; ++j) acc[i][j] += xor_popc(a[i], w[j]);
+    }
+    __syncthreads();
+  }
+
+  // ------------------------------ epilogue --------------------------------
+  // Position j*8+tn of the weight tile holds channel tn*8+j, so each thread owns
+  // 8 CONSECUTIVE output channels and stores them with 128-bit writes.
+  const int c_tile = g * p.cout_pg + tg * kBN;
+  const int valid = min(kBN, p.cout_pg - tg * kBN);
+  const int cofs = tn * 8;
+  const int c0 = c_tile + cofs;
+  const int taps = p.KH * p.KW;
+
+  float mul_r[kTN], bias_r[kTN];
+  int thr_r[kTN];
+  if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_INT8) {
+#pragma unroll
+    for (int j = 0; j < kTN; ++j) {
+      mul_r[j] = p.mul[c0 + j];
+      bias_r[j] = p.bias[c0 + j];
+    }
+  } else if (OUT == LCE_OUT_BITPACKED) {
+#pragma unroll
+    for (int j = 0; j < kTN; ++j) thr_r[j] = p.thr[c0 + j];
+  }
+  const bool full = cofs + kTN <= valid;
+
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    const long long m = m0 + warp * 16 + i * 4 + tm;
+    const bool row_ok = m < p.M;
+
+    if (p.tap_popc != nullptr && row_ok) {
+      // SAME padding with pad value 0, in integers as the reference kernel does
+      // it (reference.h:76-77,100-103): an out-of-bounds tap contributes
+      // channels_in_per_group/2 instead of popc(0 ^ w).
+      const int ohw = p.OH * p.OW;
+      const long long b = m / ohw;
+      const int r = static_cast<int>(m - b * ohw);
+      const int oy = r / p.OW;
+      const int ox = r - oy * p.OW;
+      for (int fy = 0; fy < p.KH; ++fy) {
+        const int iy = oy * p.sh - p.ph + fy * p.dh;
+        const bool yin = static_cast<unsigned>(iy) < static_cast<unsigned>(p.H);
+        for (int fx = 0; fx < p.KW; ++fx) {
+          const int ix = ox * p.sw - p.pw + fx * p.dw;
+          if (yin && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)) continue;
+          const int t = fy * p.KW + fx;
+#pragma unroll
+          for (int j = 0; j < kTN; ++j)
+            acc[i][j] += p.zp_half - p.tap_popc[static_cast<size_t>(c0 + j) * taps + t];
+        }
+      }
+    }
+
+    if (OUT == LCE_OUT_RAW_ACC) {
+      if (!row_ok) continue;
+      int* o = static_cast<int*>(p.out) + m * p.cout + c0;
+      if (full && p.vec_store) {
+        reinterpret_cast<int4*>(o)[0] = make_int4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+        reinterpret_cast<int4*>(o)[1] = make_int4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTN; ++j)
+          if (cofs + j < valid) o[j] = acc[i][j];
+      }
+    } else if (OUT == LCE_OUT_FLOAT) {
+      if (!row_ok) continue;
+      float y[kTN];
+#pragma unroll
+      for (int j = 0; j < kTN; ++j)
+        y[j] = transform_float(acc[i][j], p.clamp_min, p.clamp_max, mul_r[j], bias_r[j]);
+      float* o = static_cast<float*>(p.out) + m * p.cout + c0;
+      if (full && p.vec_store) {
+        reinterpret_cast<float4*>(o)[0] = make_float4(y[0], y[1], y[2], y[3]);
+        reinterpret_cast<float4*>(o)[1] = make_float4(y[4], y[5], y[6], y[7]);
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTN; ++j)
+          if (cofs + j < valid) o[j] = y[j];
+      }
+    } else if (OUT == LCE_OUT_INT8) {
+      if (!row_ok) continue;
+      int q[kTN];
+#pragma unroll
+      for (int j = 0; j < kTN; ++j)
+        q[j] = round_saturate_i8(
+            transform_float(acc[i][j], p.clamp_min, p.clamp_max, mul_r[j], bias_r[j]));
+      int8_t* o = static_cast<int8_t*>(p.out) + m * p.cout + c0;
+      if (full && p.vec_store) {
+        uint2 v;
+        v.x = (q[0] & 0xFF) | ((q[1] & 0xFF) << 8) | ((q[2] & 0xFF) << 16) |
+              (static_cast<uint32_t>(q[3] & 0xFF) << 24);
+        v.y = (q[4] & 0xFF) | ((q[5] & 0xFF) << 8) | ((q[6] & 0xFF) << 16) |
+              (static_cast<uint32_t>(q[7] & 0xFF) << 24);
+        *reinterpret_cast<uint2*>(o) = v;
+      } else {
+#pragma unroll
+        for (int j = 0; j < kTN; ++j)
+          if (cofs + j < valid) o[j] = static_cast<int8_t>(q[j]);
+      }
+    } else {  // LCE_OUT_BITPACKED: bit = acc > threshold (output_transform.h:164-167)
+      uint32_t bits = 0;
+#pragma unroll
+      for (int j = 0; j < kTN; ++j)
+        if (cofs + j < valid && acc[i][j] > thr_r[j]) bits |= 1u << j;
+      if (p.bp_fast) {
+        // four neighbouring lanes hold the four bytes of one output word
+        uint32_t v = bits << (8 * (tn & 3));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        const int q = tn >> 2;
+        if (row_ok && (tn & 3) == 0 && q * 32 < valid)
+          static_cast<int32_t*>(p.out)[m * p.cw_out + (c_tile >> 5) + q] =
+              static_cast<int32_t>(v);
+      } else if (row_ok && bits) {
+        // groups whose channel count is not a multiple of 32: words are shared
+        // between tiles; the host zero-fills the output first.
+#pragma unroll
+        for (int j = 0; j < kTN; ++j)
+          if (bits & (1u << j)) {
+            const int c = c0 + j;
+            atomicOr(reinterpret_cast<unsigned int*>(p.out) + m * p.cw_out + (c >> 5),
+                     1u << (c & 31));
+          }
+      }
+    }
+  }
+}
+
+// Re-lay the OHWI-packed filter [cout][taps][Cw_pg] into the kernel's tiles:
+// wt[n_tile][kv][pos][V], pos = j*8+tn <-> channel tn*8+j of the tile, zero for
+// channels past the group's end. Runs once per plan ("weights are static").
+__global__ void tile_weights_kernel(const int32_t* __restrict__ filter, int32_t* __restrict__ wt,
+                                    int cout_pg, int tiles_per_group, int taps, int Cw_pg, int V,
+                                    int Kv, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int v = static_cast<int>(idx % V);
+  long long r = idx / V;
+  const int pos = static_cast<int>(r % kBN);
+  r /= kBN;
+  const int kv = static_cast<int>(r % Kv);
+  const int nt = static_cast<int>(r / Kv);
+  const int g = nt / tiles_per_group, tg = nt - g * tiles_per_group;
+  const int ch = tg * kBN + (pos & 7) * 8 + (pos >> 3);
+  int32_t val = 0;
+  if (ch < cout_pg) {
+    const int CwV = Cw_pg / V;
+    const int tap = kv / CwV, cv = kv - tap * CwV;
+    const long long c = static_cast<long long>(g) * cout_pg + ch;
+    val = filter[(c * taps + tap) * Cw_pg + cv * V + v];
+  }
+  wt[idx] = val;
+}
+
+// tap_popc[c][t] = sum over the packed channel words of popc(filter[c][t][:]).
+__global__ void tap_popc_kernel(const int32_t* __restrict__ filter, int32_t* __restrict__ out,
+                                int cout, int taps, int Cw_pg) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * taps) return;
+  const int32_t* f = filter + static_cast<size_t>(idx) * Cw_pg;
+  int s = 0;
+  for (int w = 0; w < Cw_pg; ++w) s += __popc(static_cast<uint32_t>(f[w]));
+  out[idx] = s;
+}
+
+// ------------------------------------------------------------------------- //
+// K1: bsign_pack (LceQuantize). bit = value < zero_point (float: value < 0, so
+// -0.0 and NaN pack as 0 and negative denormals as 1: compiled WITHOUT -ftz).
+// Fast path (cols % 32 == 0, float): the tensor is one flat array; each thread
+// converts 8 consecutive floats (two 128-bit loads) into one byte, four lanes
+// assemble a word with two shuffles. HBM-bound: 4 B read + 1/8 B written / elem.
+// ------------------------------------------------------------------------- //
+__device__ __forceinline__ uint32_t sign_nibble(const float4& f) {
+  return (f.x < 0.0f ? 1u : 0u) | (f.y < 0.0f ? 2u : 0u) | (f.z < 0.0f ? 4u : 0u) |
+         (f.w < 0.0f ? 8u : 0u);
+}
+
+__global__ void __launch_bounds__(256) pack_f32_flat_kernel(const float4* __restrict__ in,
+                                                            int32_t* __restrict__ out,
+                                                            long long n_words) {
+  // thread t handles floats [8t, 8t+8): lanes 4q..4q+3 form word q of the warp.
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n_threads_needed = n_words * 4;
+  for (long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+       t - (threadIdx.x & 31) < n_threads_needed; t += stride) {
+    uint32_t byte = 0;
+    if (t < n_threads_needed) {
+      const float4 a = __ldcs(in + 2 * t);
+      const float4 b = __ldcs(in + 2 * t + 1);
+      byte = sign_nibble(a) | (sign_nibble(b) << 4);
+    }
+    uint32_t v = byte << (8 * (threadIdx.x & 3));
+    v |= __shfl_xor_sync(0xffffffffu, v, 1);
+    v |= __shfl_xor_sync(0xffffffffu, v, 2);
+    if ((threadIdx.x & 3) == 0 && t < n_threads_needed) out[t >> 2] = static_cast<int32_t>(v);
+  }
+}
+
+// General path: one warp per output word, lane i tests element 32w+i (ballot);
+// elements past `cols` behave as zero_point (bit 0): bitpack.h:238-244.
+template <typename T>
+__device__ __forceinline__ bool below_zero_point(T x, int zp);
+template <>
+__device__ __forceinline__ bool below_zero_point<float>(float x, int) { return x < 0.0f; }
+template <>
+__device__ __forceinline__ bool below_zero_point<int8_t>(int8_t x, int zp) {
+  return static_cast<int>(x) < zp;  // int32 compare: covers bitpack.h:259-288
+}
+template <>
+__device__ __forceinline__ bool below_zero_point<uint8_t>(uint8_t x, int zp) {
+  return static_cast<int>(x) < zp;  // bool viewed as uint8, zp = 1 (quantization.cc:88-108)
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) pack_generic_kernel(const T* __restrict__ in,
+                                                           int32_t* __restrict__ out,
+                                                           long long rows, int cols, int cw,
+                                                           int zero_point) {
+  const long long n_words = rows * cw;
+  const int lane = threadIdx.x & 31;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  for (long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+       w < n_words; w += warps) {
+    const long long r = w / cw;
+    const int c = static_cast<int>(w - r * cw) * 32 + lane;
+    bool bit = false;
+    if (c < cols) bit = below_zero_point<T>(in[r * cols + c], zero_point);
+    const uint32_t word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) out[w] = static_cast<int32_t>(word);
+  }
+}
+
+// ------------------------------------------------------------------------- //
+// K5: unpack (LceDequantize): bit 0 -> zero_bit_value, bit 1 -> one_bit_value.
+// ------------------------------------------------------------------------- //
+template <typename T>
+__global__ void __launch_bounds__(256) unpack_kernel(const int32_t* __restrict__ in,
+                                                     T* __restrict__ out, long long rows,
+                                                     int cols, int cw, T zero_bit, T one_bit) {
+  const long long n = rows * cols;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += stride) {
+    const long long r = i / cols;
+    const int c = static_cast<int>(i - r * cols);
+    const uint32_t word = static_cast<uint32_t>(in[r * cw + (c >> 5)]);
+    out[i] = ((word >> (c & 31)) & 1u) ? one_bit : zero_bit;
+  }
+}
+
+// ------------------------------------------------------------------------- //
+// K4: bmaxpool: AND over the in-bounds part of the window (bmaxpool.h:45-84).
+// One thread per output word; the channel word is the fastest index (coalesced).
+// ------------------------------------------------------------------------- //
+__global__ void __launch_bounds__(256) bmaxpool_kernel(const int32_t* __restrict__ in,
+                                                       int32_t* __restrict__ out, int B, int H,
+                                                       int W, int C, int OH, int OW, int fh,
+                                                       int fw, int sh, int sw, int ph, int pw) {
+  const long long n = static_cast<long long>(B) * OH * OW * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += stride) {
+    const int c = static_cast<int>(i % C);
+    long long r = i / C;
+    const int ox = static_cast<int>(r % OW);
+    r /= OW;
+    const int oy = static_cast<int>(r % OH);
+    const int b = static_cast<int>(r / OH);
+    const int y0 = oy * sh - ph, x0 = ox * sw - pw;
+    const int ys = max(0, y0), ye = min(H, y0 + fh);
+    const int xs = max(0, x0), xe = min(W, x0 + fw);
+    int32_t m = ~0;
+    for (int y = ys; y < ye; ++y)
+      for (int x = xs; x < xe; ++x)
+        m &= in[((static_cast<long long>(b) * H + y) * W + x) * C + c];
+    out[i] = m;
+  }
+}
+
+}  // namespace lce
