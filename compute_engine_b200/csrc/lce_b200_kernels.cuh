@@ -115,6 +115,40 @@ __device__ __forceinline__ int xor_popc(const uint4& a, const uint4& b) {
   return __popc(a.x ^ b.x) + __popc(a.y ^ b.y) + __popc(a.z ^ b.z) + __popc(a.w ^ b.w);
 }
 
+
+template <int V>
+__device__ __forceinline__ void load_words(const typename VecT<V>::T* p, uint32_t* dst);
+template <>
+__device__ __forceinline__ void load_words<1>(const uint32_t* p, uint32_t* dst) { dst[0] = *p; }
+template <>
+__device__ __forceinline__ void load_words<2>(const uint2* p, uint32_t* dst) {
+  const uint2 v = *p;
+  dst[0] = v.x; dst[1] = v.y;
+}
+template <>
+__device__ __forceinline__ void load_words<4>(const uint4* p, uint32_t* dst) {
+  const uint4 v = *p;
+  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
+}
+
+// Carry-save adder on bit-planes: a + b + c = s + 2*cy, two LOP3s.
+__device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s,
+                                    uint32_t& cy) {
+  s = a ^ b ^ c;
+  cy = (a & b) | (c & (a ^ b));
+}
+// sum_k popc(a[k] ^ w[k]) over 8 words with 4 POPCs:
+//   x0+x1+x2 = s1+2c1, x3+x4+x5 = s2+2c2, s1+s2+x6 = s3+2c3, c1+c2+c3 = s4+2c4
+//   => total = popc(s3) + popc(x7) + 2*popc(s4) + 4*popc(c4)      (exact integers)
+__device__ __forceinline__ int xor_popc8(const uint32_t* a, const uint32_t* w) {
+  uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
+  csa(a[0] ^ w[0], a[1] ^ w[1], a[2] ^ w[2], s1, c1);
+  csa(a[3] ^ w[3], a[4] ^ w[4], a[5] ^ w[5], s2, c2);
+  csa(s1, s2, a[6] ^ w[6], s3, c3);
+  csa(c1, c2, c3, s4, c4);
+  return __popc(s3) + __popc(a[7] ^ w[7]) + 2 * __popc(s4) + 4 * __popc(c4);
+}
+
 // OutputTransform<float>::Run, output_transform.h:100-106: shift, int32 clamp,
 // int->float, then an UNFUSED multiply and add (two roundings).
 __device__ __forceinline__ float transform_float(int acc, int cmin, int cmax, float mul,
@@ -228,8 +262,28 @@ __global__ void __launch_bounds__(kThreads, 2) bconv_kernel(const ConvKParams p)
     const Vec* a_ptr = A_s + warp * 16 + tm;
     const Vec* w_ptr = W_s + tn;
     const int nkv = kv1 - kv0;
-#pragma unroll(V == 4 ? 1 : (V == 2 ? 2 : 4))
-    for (int kv = 0; kv < nkv; ++kv) {
+    // Main loop: 8 K-words at a time through a carry-save adder tree, so that 8
+    // XOR words cost 4 POPCs (XU pipe, 16/clk/SM) + 16 LOP3s (ALU pipe, 64/clk/SM)
+    // instead of 8 POPCs -- the two pipes issue side by side (measured:
+    // profiles/r01_microbench_pipes.jsonl).
+    constexpr int G = 8 / V;  // smem vectors per 8-word group
+    int kv = 0;
+    for (; kv + G <= nkv; kv += G) {
+      uint32_t a[kTM][8];
+#pragma unroll
+      for (int i = 0; i < kTM; ++i)
+#pragma unroll
+        for (int gq = 0; gq < G; ++gq) load_words<V>(a_ptr + (kv + gq) * kBM + i * 4, &a[i][gq * V]);
+#pragma unroll
+      for (int j = 0; j < kTN; ++j) {
+        uint32_t w[8];
+#pragma unroll
+        for (int gq = 0; gq < G; ++gq) load_words<V>(w_ptr + (kv + gq) * kBN + j * 8, &w[gq * V]);
+#pragma unroll
+        for (int i = 0; i < kTM; ++i) acc[i][j] += xor_popc8(a[i], w);
+      }
+    }
+    for (; kv < nkv; ++kv) {  // K tail (< 8 words): plain XOR + POPC
       Vec a[kTM], w[kTN];
 #pragma unroll
       for (int i = 0; i < kTM; ++i) a[i] = a_ptr[kv * kBM + i * 4];
