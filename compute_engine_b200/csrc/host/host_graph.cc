@@ -1,0 +1,427 @@
+#include "host_graph.h"
+
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace lce_b200 {
+
+namespace {
+size_t TypeSize(TfLiteType t) {
+  switch (t) {
+    case kTfLiteFloat32: return 4;
+    case kTfLiteInt32: return 4;
+    case kTfLiteInt64: return 8;
+    case kTfLiteUInt8:
+    case kTfLiteInt8:
+    case kTfLiteBool: return 1;
+    default: return 0;
+  }
+}
+TfLiteIntArray* MakeDims(const std::vector<int>& d) {
+  TfLiteIntArray* a = LceB200IntArrayCreate(static_cast<int>(d.size()));
+  for (size_t i = 0; i < d.size(); ++i) a->data[i] = d[i];
+  return a;
+}
+size_t BytesOf(const TfLiteTensor& t) {
+  size_t n = TypeSize(t.type);
+  for (int i = 0; i < t.dims->size; ++i) n *= static_cast<size_t>(std::max(t.dims->data[i], 0));
+  return n;
+}
+constexpr size_t kAlign = 256;
+size_t AlignUp(size_t x) { return (x + kAlign - 1) / kAlign * kAlign; }
+}  // namespace
+
+// ------------------------------ OpResolver ------------------------------- //
+void OpResolver::AddCustom(const char* name, const TfLiteRegistration* r) { custom_[name] = r; }
+void OpResolver::AddBuiltin(int code, const TfLiteRegistration* r) { builtin_[code] = r; }
+const TfLiteRegistration* OpResolver::FindCustom(const std::string& name) const {
+  auto it = custom_.find(name);
+  return it == custom_.end() ? nullptr : it->second;
+}
+const TfLiteRegistration* OpResolver::FindBuiltin(int code) const {
+  auto it = builtin_.find(code);
+  return it == builtin_.end() ? nullptr : it->second;
+}
+
+// --------------------------------- Graph --------------------------------- //
+Graph::Graph(bool device_arena) : device_arena_(device_arena) {
+  memset(&ctx_, 0, sizeof(ctx_));
+  ctx_.impl_ = this;
+  ctx_.ResizeTensor = &Graph::ResizeTensorCb;
+  ctx_.ReportError = &Graph::ReportErrorCb;
+  ctx_.AddTensors = &Graph::AddTensorsCb;
+  ctx_.GetTensor = &Graph::GetTensorCb;
+  ctx_.GetExternalContext = &Graph::GetExternalContextCb;
+  ctx_.SetExternalContext = &Graph::SetExternalContextCb;
+  ctx_.recommended_num_threads = 1;
+  if (device_arena_) {
+    cudaStream_t s = nullptr;
+    if (cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking) == cudaSuccess) stream_ = s;
+    else cudaGetLastError();
+  }
+}
+
+Graph::~Graph() {
+  for (auto& n : nodes_) {
+    if (n->initialized && n->registration->free) n->registration->free(&ctx_, n->node.user_data);
+    LceB200IntArrayFree(n->node.inputs);
+    LceB200IntArrayFree(n->node.outputs);
+    LceB200IntArrayFree(n->node.temporaries);
+    LceB200IntArrayFree(n->node.intermediates);
+  }
+  if (graph_exec_) cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec_));
+  FreeArena();
+  for (void* p : const_dev_)
+    if (p) cudaFree(p);
+  for (auto& t : tensors_) {
+    LceB200IntArrayFree(t.dims);
+    if (t.quantization.params) {
+      auto* q = static_cast<TfLiteAffineQuantization*>(t.quantization.params);
+      free(q->scale);
+      LceB200IntArrayFree(q->zero_point);
+      free(q);
+    }
+  }
+  if (stream_) cudaStreamDestroy(static_cast<cudaStream_t>(stream_));
+}
+
+void Graph::RefreshContext() {
+  ctx_.tensors = tensors_.data();
+  ctx_.tensors_size = tensors_.size();
+}
+
+int Graph::AddTensor(TfLiteType type, const std::vector<int>& dims, const void* const_data,
+                     size_t const_bytes, bool has_quant, float scale, int zero_point,
+                     const std::string& name, bool const_on_device) {
+  TfLiteTensor t;
+  memset(&t, 0, sizeof(t));
+  t.type = type;
+  t.dims = MakeDims(dims);
+  t.params.scale = scale;
+  t.params.zero_point = zero_point;
+  if (has_quant) {
+    auto* q = static_cast<TfLiteAffineQuantization*>(malloc(sizeof(TfLiteAffineQuantization)));
+    q->scale = static_cast<TfLiteFloatArray*>(malloc(sizeof(TfLiteFloatArray) + sizeof(float)));
+    q->scale->size = 1;
+    q->scale->data[0] = scale;
+    q->zero_point = LceB200IntArrayCreate(1);
+    q->zero_point->data[0] = zero_point;
+    q->quantized_dimension = 0;
+    t.quantization.type = kTfLiteAffineQuantization;
+    t.quantization.params = q;
+  }
+  t.bytes = BytesOf(t);
+  names_.push_back(name);
+  const_host_.emplace_back();
+  const_dev_.push_back(nullptr);
+  const int idx = static_cast<int>(tensors_.size());
+  if (const_data) {
+    auto& h = const_host_.back();
+    h.assign(static_cast<const uint8_t*>(const_data),
+             static_cast<const uint8_t*>(const_data) + const_bytes);
+    h.resize(const_bytes + 64, 0);  // slack: kernels may read whole vectors
+    t.allocation_type = kTfLiteMmapRo;
+    t.data.raw = reinterpret_cast<char*>(h.data());
+    t.bytes = const_bytes;
+    if (const_on_device && device_arena_) {
+      void* d = nullptr;
+      if (cudaMalloc(&d, const_bytes + 64) == cudaSuccess &&
+          cudaMemcpy(d, h.data(), const_bytes + 64, cudaMemcpyHostToDevice) == cudaSuccess) {
+        const_dev_.back() = d;
+        t.data.raw = static_cast<char*>(d);
+      } else {
+        cudaGetLastError();
+      }
+    }
+  } else {
+    t.allocation_type = kTfLiteArenaRw;
+  }
+  tensors_.push_back(t);
+  tensors_.back().name = names_.back().c_str();
+  for (size_t i = 0; i < tensors_.size(); ++i) tensors_[i].name = names_[i].c_str();
+  RefreshContext();
+  allocated_ = false;
+  return idx;
+}
+
+int Graph::AddNode(const TfLiteRegistration* registration, const std::vector<int>& inputs,
+                   const std::vector<int>& outputs, const uint8_t* custom_options,
+                   size_t options_len, const void* builtin_data, size_t builtin_bytes,
+                   const std::string& name) {
+  auto rec = std::make_unique<NodeRecord>();
+  rec->registration = registration;
+  rec->name = name;
+  if (custom_options) rec->custom_options.assign(custom_options, custom_options + options_len);
+  if (builtin_data)
+    rec->builtin_blob.assign(static_cast<const uint8_t*>(builtin_data),
+                             static_cast<const uint8_t*>(builtin_data) + builtin_bytes);
+  rec->node.inputs = MakeDims(inputs);
+  rec->node.outputs = MakeDims(outputs);
+  rec->node.temporaries = LceB200IntArrayCreate(0);
+  rec->node.intermediates = LceB200IntArrayCreate(0);
+  rec->node.custom_initial_data = rec->custom_options.data();
+  rec->node.custom_initial_data_size = static_cast<int>(rec->custom_options.size());
+  rec->node.builtin_data = rec->builtin_blob.empty() ? nullptr : rec->builtin_blob.data();
+  nodes_.push_back(std::move(rec));
+  allocated_ = false;
+  return static_cast<int>(nodes_.size()) - 1;
+}
+
+TfLiteStatus Graph::ResizeTensorCb(TfLiteContext* c, TfLiteTensor* t, TfLiteIntArray* new_size) {
+  // Takes ownership of new_size (common.h: ResizeTensor contract).
+  auto* g = static_cast<Graph*>(c->impl_);
+  if (t->allocation_type == kTfLiteMmapRo) {
+    LceB200IntArrayFree(new_size);
+    g->error_ = "ResizeTensor called on a constant tensor";
+    return kTfLiteError;
+  }
+  LceB200IntArrayFree(t->dims);
+  t->dims = new_size;
+  t->bytes = BytesOf(*t);
+  g->allocated_ = false;
+  return kTfLiteOk;
+}
+
+void Graph::ReportErrorCb(TfLiteContext* c, const char* msg, ...) {
+  auto* g = static_cast<Graph*>(c->impl_);
+  char buf[1024];
+  va_list ap;
+  va_start(ap, msg);
+  vsnprintf(buf, sizeof(buf), msg, ap);
+  va_end(ap);
+  g->error_ = buf;
+}
+
+TfLiteStatus Graph::AddTensorsCb(TfLiteContext* c, int n, int* first) {
+  auto* g = static_cast<Graph*>(c->impl_);
+  if (first) *first = static_cast<int>(g->tensors_.size());
+  for (int i = 0; i < n; ++i)
+    g->AddTensor(kTfLiteNoType, {0}, nullptr, 0, false, 0.f, 0, "temporary");
+  return kTfLiteOk;
+}
+
+TfLiteTensor* Graph::GetTensorCb(const TfLiteContext* c, int i) {
+  auto* g = static_cast<Graph*>(c->impl_);
+  if (i < 0 || i >= static_cast<int>(g->tensors_.size())) return nullptr;
+  return &g->tensors_[i];
+}
+
+TfLiteExternalContext* Graph::GetExternalContextCb(TfLiteContext* c, TfLiteExternalContextType t) {
+  auto* g = static_cast<Graph*>(c->impl_);
+  return (t >= 0 && t < kTfLiteMaxExternalContexts) ? g->external_[t] : nullptr;
+}
+void Graph::SetExternalContextCb(TfLiteContext* c, TfLiteExternalContextType t,
+                                 TfLiteExternalContext* e) {
+  auto* g = static_cast<Graph*>(c->impl_);
+  if (t >= 0 && t < kTfLiteMaxExternalContexts) g->external_[t] = e;
+}
+
+void Graph::FreeArena() {
+  if (!arena_) return;
+  if (device_arena_) cudaFree(arena_);
+  else free(arena_);
+  arena_ = nullptr;
+  arena_bytes_ = 0;
+}
+
+// Greedy-by-size offset assignment over tensor lifetimes (the idea of TFLite's
+// arena planner): tensors whose [first_use, last_use] node ranges are disjoint may
+// share bytes. Graph inputs live from -1, graph outputs until the end.
+TfLiteStatus Graph::PlanArena() {
+  const int n_nodes = static_cast<int>(nodes_.size());
+  const int n_t = static_cast<int>(tensors_.size());
+  std::vector<int> first(n_t, n_nodes + 1), last(n_t, -2);
+  auto touch = [&](int t, int when) {
+    if (t < 0 || t >= n_t) return;
+    first[t] = std::min(first[t], when);
+    last[t] = std::max(last[t], when);
+  };
+  for (int t : inputs_) touch(t, -1);
+  for (int i = 0; i < n_nodes; ++i) {
+    const TfLiteNode& nd = nodes_[i]->node;
+    for (int k = 0; k < nd.inputs->size; ++k) touch(nd.inputs->data[k], i);
+    for (int k = 0; k < nd.outputs->size; ++k) touch(nd.outputs->data[k], i);
+    for (int k = 0; k < nd.temporaries->size; ++k) touch(nd.temporaries->data[k], i);
+  }
+  for (int t : outputs_) touch(t, n_nodes);
+  struct Item { int t; size_t bytes; size_t off; };
+  std::vector<Item> items;
+  for (int t = 0; t < n_t; ++t) {
+    if (tensors_[t].allocation_type != kTfLiteArenaRw || last[t] < -1) continue;
+    items.push_back({t, AlignUp(std::max<size_t>(tensors_[t].bytes, 1) + 64), 0});
+  }
+  std::sort(items.begin(), items.end(),
+            [](const Item& a, const Item& b) { return a.bytes > b.bytes; });
+  std::vector<Item> placed;
+  size_t total = 0;
+  for (auto& it : items) {
+    std::vector<std::pair<size_t, size_t>> busy;
+    for (auto& p : placed)
+      if (!(last[p.t] < first[it.t] || last[it.t] < first[p.t]))
+        busy.emplace_back(p.off, p.off + p.bytes);
+    std::sort(busy.begin(), busy.end());
+    size_t off = 0;
+    for (auto& b : busy) {
+      if (off + it.bytes <= b.first) break;
+      off = std::max(off, b.second);
+    }
+    it.off = off;
+    placed.push_back(it);
+    total = std::max(total, off + it.bytes);
+  }
+  if (total > arena_bytes_) {
+    FreeArena();
+    if (device_arena_) {
+      if (cudaMalloc(&arena_, total) != cudaSuccess) {
+        error_ = std::string("cudaMalloc of the tensor arena failed: ") +
+                 cudaGetErrorString(cudaGetLastError());
+        return kTfLiteError;
+      }
+    } else {
+      arena_ = malloc(total);
+      if (!arena_) return kTfLiteError;
+    }
+    arena_bytes_ = total;
+  }
+  for (auto& p : placed) tensors_[p.t].data.raw = static_cast<char*>(arena_) + p.off;
+  return kTfLiteOk;
+}
+
+TfLiteStatus Graph::AllocateTensors() {
+  RefreshContext();
+  if (graph_exec_) {
+    cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec_));
+    graph_exec_ = nullptr;
+  }
+  for (auto& n : nodes_) {
+    if (!n->initialized) {
+      if (n->registration->init) {
+        const char* buf = n->node.builtin_data
+                              ? static_cast<const char*>(n->node.builtin_data)
+                              : reinterpret_cast<const char*>(n->custom_options.data());
+        const size_t len = n->node.builtin_data ? n->builtin_blob.size() : n->custom_options.size();
+        n->node.user_data = n->registration->init(&ctx_, buf, len);
+      }
+      n->initialized = true;
+    }
+    if (n->registration->prepare) {
+      if (n->registration->prepare(&ctx_, &n->node) != kTfLiteOk) {
+        if (error_.empty()) error_ = "prepare failed for node " + n->name;
+        return kTfLiteError;
+      }
+      RefreshContext();
+    }
+  }
+  if (PlanArena() != kTfLiteOk) return kTfLiteError;
+  allocated_ = true;
+  warmed_ = false;
+  return kTfLiteOk;
+}
+
+TfLiteStatus Graph::ResizeInputTensor(int t, const std::vector<int>& dims) {
+  if (t < 0 || t >= static_cast<int>(tensors_.size())) return kTfLiteError;
+  return ResizeTensorCb(&ctx_, &tensors_[t], MakeDims(dims));
+}
+
+TfLiteStatus Graph::EnableCudaGraph(bool on) {
+  use_cuda_graph_ = on && device_arena_;
+  if (!use_cuda_graph_ && graph_exec_) {
+    cudaGraphExecDestroy(static_cast<cudaGraphExec_t>(graph_exec_));
+    graph_exec_ = nullptr;
+  }
+  return kTfLiteOk;
+}
+
+TfLiteStatus Graph::Invoke() {
+  if (!allocated_ && AllocateTensors() != kTfLiteOk) return kTfLiteError;
+  if (device_arena_) lce_b200_set_stream(stream_);
+  auto run_nodes = [&]() -> TfLiteStatus {
+    for (auto& n : nodes_) {
+      if (n->registration->invoke(&ctx_, &n->node) != kTfLiteOk) {
+        if (error_.empty()) error_ = "invoke failed for node " + n->name;
+        return kTfLiteError;
+      }
+    }
+    return kTfLiteOk;
+  };
+  if (!use_cuda_graph_) return run_nodes();
+  cudaStream_t s = static_cast<cudaStream_t>(stream_);
+  if (!graph_exec_) {
+    // First call runs eagerly (ops build their plans: allocations are not
+    // capturable); the second call records the launch sequence.
+    if (!warmed_) {
+      warmed_ = true;
+      return run_nodes();
+    }
+    cudaGraph_t graph = nullptr;
+    if (cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) != cudaSuccess) {
+      cudaGetLastError();
+      return run_nodes();
+    }
+    TfLiteStatus rc = run_nodes();
+    if (cudaStreamEndCapture(s, &graph) != cudaSuccess || rc != kTfLiteOk || !graph) {
+      cudaGetLastError();
+      error_ = "CUDA graph capture failed";
+      return kTfLiteError;
+    }
+    cudaGraphExec_t exec = nullptr;
+    if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) {
+      cudaGraphDestroy(graph);
+      error_ = "cudaGraphInstantiate failed";
+      return kTfLiteError;
+    }
+    cudaGraphDestroy(graph);
+    graph_exec_ = exec;
+  }
+  if (cudaGraphLaunch(static_cast<cudaGraphExec_t>(graph_exec_), s) != cudaSuccess) {
+    error_ = "cudaGraphLaunch failed";
+    return kTfLiteError;
+  }
+  return kTfLiteOk;
+}
+
+TfLiteStatus Graph::WriteTensor(int i, const void* src, size_t bytes) {
+  TfLiteTensor& t = tensors_[i];
+  if (bytes > t.bytes || !t.data.raw) {
+    error_ = "WriteTensor: size mismatch or unallocated tensor";
+    return kTfLiteError;
+  }
+  if (device_arena_ && t.allocation_type == kTfLiteArenaRw) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    if (cudaMemcpyAsync(t.data.raw, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+      error_ = "WriteTensor: H2D copy failed";
+      return kTfLiteError;
+    }
+  } else {
+    memcpy(t.data.raw, src, bytes);
+  }
+  return kTfLiteOk;
+}
+
+TfLiteStatus Graph::ReadTensor(int i, void* dst, size_t bytes) {
+  TfLiteTensor& t = tensors_[i];
+  if (bytes > t.bytes || !t.data.raw) {
+    error_ = "ReadTensor: size mismatch or unallocated tensor";
+    return kTfLiteError;
+  }
+  if (device_arena_ && t.allocation_type == kTfLiteArenaRw) {
+    cudaStream_t s = static_cast<cudaStream_t>(stream_);
+    if (cudaMemcpyAsync(dst, t.data.raw, bytes, cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      error_ = std::string("ReadTensor: D2H copy failed: ") +
+               cudaGetErrorString(cudaGetLastError());
+      return kTfLiteError;
+    }
+  } else {
+    memcpy(dst, const_host_[i].empty() ? t.data.raw : reinterpret_cast<char*>(const_host_[i].data()),
+           bytes);
+  }
+  return kTfLiteOk;
+}
+
+}  // namespace lce_b200
