@@ -230,27 +230,17 @@ def main_b200(args):
 
     B = args.batch
     # ---- load: rank 0 owns the model; ONE broadcast of the packed weights -------
+    from compute_engine_b200 import parallel
     layers = make_stack_weights(0) if rank == 0 else None
-    shapes = [(c, hw) for (hw, c) in STAGES for _ in range(LAYERS_PER_STAGE)]
-    blob_words = sum(c * 9 * (c // 32) + 2 * c for c, _ in shapes)
-    blob = torch.empty(blob_words, dtype=torch.int32, device=dev)
     if rank == 0:
-        parts = []
-        for lay in layers:
-            parts += [lay["filter"].reshape(-1), lay["mul"].view(np.int32), lay["bias"].view(np.int32)]
-        blob.copy_(torch.from_numpy(np.concatenate(parts)))
-    if world > 1:
-        dist.broadcast(blob, src=0)        # the only collective; none on the step path
-    plans, off = [], 0
-    for c, hw in shapes:
-        nf = c * 9 * (c // 32)
-        filt = blob[off:off + nf].view(c, 3, 3, c // 32)
-        mul = blob[off + nf:off + nf + c].view(torch.float32)
-        bias = blob[off + nf + c:off + nf + 2 * c].view(torch.float32)
-        off += nf + 2 * c
+        layers = [{"filter": l["filter"], "mul": l["mul"], "bias": l["bias"]} for l in layers]
+    dev_layers, blob = parallel.broadcast_model(layers, dev)   # the only collective; none per step
+    shapes = [(c, hw) for (hw, c) in STAGES for _ in range(LAYERS_PER_STAGE)]
+    plans = []
+    for (c, hw), lay in zip(shapes, dev_layers):
         d = capi.BconvDesc(B, hw, hw, c, 3, 3, c, 1, 1, 1, 1, 1, capi.PADDING_SAME, 1,
                            capi.ACT_RELU, capi.OUT_FLOAT, 1.0, 0)
-        plans.append(capi.BConv2d(d, filt, mul, bias))
+        plans.append(capi.BConv2d(d, lay["filter"], lay["mul"], lay["bias"]))
 
     # ---- per-rank shard of the batch (images are independent) -------------------
     host_in = [torch.from_numpy(x).pin_memory() for x in make_stage_inputs(B, 100 + rank)]

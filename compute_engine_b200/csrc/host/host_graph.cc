@@ -339,7 +339,7 @@ TfLiteStatus Graph::EnableCudaGraph(bool on) {
 
 TfLiteStatus Graph::Invoke() {
   if (!allocated_ && AllocateTensors() != kTfLiteOk) return kTfLiteError;
-  if (device_arena_) lce_b200_set_stream(stream_);
+  lce_b200_set_stream(stream_);  // nullptr (legacy default stream) for a host arena
   auto run_nodes = [&]() -> TfLiteStatus {
     for (auto& n : nodes_) {
       if (n->registration->invoke(&ctx_, &n->node) != kTfLiteOk) {

@@ -122,19 +122,25 @@ TfLiteStatus WithDeviceIO(TfLiteContext* ctx, Staging* st, const TfLiteTensor* i
   if (!in_dev) {
     if (input->bytes &&
         cudaMemcpyAsync(st->in, input->data.raw_const, input->bytes, cudaMemcpyHostToDevice, s) !=
-            cudaSuccess)
+            cudaSuccess) {
+      ctx->ReportError(ctx, "lce_b200: H2D staging copy failed: %s",
+                       cudaGetErrorString(cudaGetLastError()));
       return kTfLiteError;
+    }
     din = st->in;
   }
   if (!out_dev) dout = st->out;
   TfLiteStatus rc = launch(din, dout);
   if (rc != kTfLiteOk) return rc;
   if (!out_dev) {
-    if (output->bytes &&
-        cudaMemcpyAsync(output->data.raw, st->out, output->bytes, cudaMemcpyDeviceToHost, s) !=
-            cudaSuccess)
+    if ((output->bytes &&
+         cudaMemcpyAsync(output->data.raw, st->out, output->bytes, cudaMemcpyDeviceToHost, s) !=
+             cudaSuccess) ||
+        cudaStreamSynchronize(s) != cudaSuccess) {
+      ctx->ReportError(ctx, "lce_b200: D2H staging copy failed: %s",
+                       cudaGetErrorString(cudaGetLastError()));
       return kTfLiteError;
-    if (cudaStreamSynchronize(s) != cudaSuccess) return kTfLiteError;
+    }
   }
   return kTfLiteOk;
 }
