@@ -45,7 +45,8 @@ def build_cuda(force=False, verbose=False):
            [os.path.join(INC, f) for f in os.listdir(INC)]
     if not force and not _newer(out, srcs):
         return out
-    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INC, os.path.join(CSRC, "lce_b200.cu"), "-o", out]
+    cus = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
+    cmd = [_nvcc(), *NVCC_FLAGS, "-I", INC, *cus, "-o", out]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

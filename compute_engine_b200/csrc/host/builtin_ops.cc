@@ -1,8 +1,309 @@
-// builtin_ops.cc -- float TFLite builtins the three model families need around the
-// binary path. Placeholder registration point; the ops are added as
-// the graph host widens.
+// builtin_ops.cc -- TfLiteRegistrations for the float builtins QuickNet /
+// QuickNetLarge / Bi-RealNet-18 use around the binary path, backed by
+// the fp32 CUDA kernels of lce_b200_builtins.cu. Shape inference follows TFLite's
+// builtin kernels (tensorflow/lite/kernels/{conv,depthwise_conv,pooling,add,mul,
+// fully_connected,softmax,reduce,reshape,activations}.cc). Device arena only.
+#include <cuda_runtime.h>
+
+#include <cstring>
+
+#include "builtin_params.h"
 #include "host_graph.h"
+#include "lce_b200.h"
+#include "lce_b200_builtins.h"
 
 namespace lce_b200 {
-void RegisterBuiltinOps(OpResolver*) {}
+namespace {
+
+#define B_ENSURE(ctx, cond, msg)                 \
+  do {                                           \
+    if (!(cond)) {                               \
+      (ctx)->ReportError((ctx), "%s", (msg));    \
+      return kTfLiteError;                       \
+    }                                            \
+  } while (0)
+#define B_CAPI(ctx, call)                                     \
+  do {                                                        \
+    if ((call) != 0) {                                        \
+      (ctx)->ReportError((ctx), "%s", lce_b200_last_error()); \
+      return kTfLiteError;                                    \
+    }                                                         \
+  } while (0)
+
+TfLiteTensor* T(TfLiteContext* c, const TfLiteIntArray* a, int i) {
+  if (i >= a->size || a->data[i] < 0) return nullptr;
+  return &c->tensors[a->data[i]];
+}
+int64_t Count(const TfLiteTensor* t) {
+  int64_t n = 1;
+  for (int i = 0; i < t->dims->size; ++i) n *= t->dims->data[i];
+  return n;
+}
+TfLiteStatus Resize(TfLiteContext* c, TfLiteTensor* t, std::initializer_list<int> dims) {
+  TfLiteIntArray* a = LceB200IntArrayCreate(static_cast<int>(dims.size()));
+  int i = 0;
+  for (int d : dims) a->data[i++] = d;
+  return c->ResizeTensor(c, t, a);
+}
+bool OnDevice(const void* p) {
+  cudaPointerAttributes a;
+  if (!p || cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged;
+}
+
+void* Init(TfLiteContext*, const char* buffer, size_t length) {
+  auto* p = new BuiltinParams();
+  memset(p, 0, sizeof(*p));
+  if (buffer && length >= sizeof(BuiltinParams)) memcpy(p, buffer, sizeof(BuiltinParams));
+  return p;
+}
+void Free(TfLiteContext*, void* p) { delete static_cast<BuiltinParams*>(p); }
+const BuiltinParams& P(TfLiteNode* n) { return *static_cast<BuiltinParams*>(n->user_data); }
+
+// ---------------------------- CONV_2D / DEPTHWISE ---------------------------- //
+bool ConvDesc(TfLiteContext* c, TfLiteNode* n, bool depthwise, lce_f32_conv_desc* d) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* f = T(c, n->inputs, 1);
+  if (!in || !f || in->dims->size != 4 || f->dims->size != 4) return false;
+  const BuiltinParams& p = P(n);
+  d->batch = in->dims->data[0];
+  d->in_h = in->dims->data[1];
+  d->in_w = in->dims->data[2];
+  d->in_c = in->dims->data[3];
+  d->filter_h = f->dims->data[1];
+  d->filter_w = f->dims->data[2];
+  d->out_c = depthwise ? f->dims->data[3] : f->dims->data[0];
+  d->stride_h = p.stride_h;
+  d->stride_w = p.stride_w;
+  d->dilation_h = p.dilation_h;
+  d->dilation_w = p.dilation_w;
+  d->padding = p.padding;
+  d->activation = p.activation;
+  if (!depthwise && f->dims->data[3] != d->in_c) return false;
+  return true;
+}
+template <bool DW>
+TfLiteStatus ConvPrepare(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_conv_desc d;
+  B_ENSURE(c, ConvDesc(c, n, DW, &d), "CONV_2D: bad input / filter shapes");
+  B_ENSURE(c, T(c, n->inputs, 0)->type == kTfLiteFloat32, "CONV_2D: only float32 is supported");
+  if (DW) B_ENSURE(c, P(n).depth_multiplier == 1 && d.out_c == d.in_c,
+                   "DEPTHWISE_CONV_2D: depth_multiplier must be 1");
+  int oh, ow;
+  B_CAPI(c, lce_b200_f32_conv_out_shape(&d, &oh, &ow));
+  return Resize(c, T(c, n->outputs, 0), {d.batch, oh, ow, d.out_c});
+}
+template <bool DW>
+TfLiteStatus ConvInvoke(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_conv_desc d;
+  ConvDesc(c, n, DW, &d);
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* f = T(c, n->inputs, 1);
+  const TfLiteTensor* bias = T(c, n->inputs, 2);
+  TfLiteTensor* out = T(c, n->outputs, 0);
+  B_ENSURE(c, OnDevice(in->data.raw) && OnDevice(f->data.raw) && OnDevice(out->data.raw),
+           "float builtins need a device arena (no CPU path)");
+  if (DW)
+    B_CAPI(c, lce_b200_f32_depthwise_conv2d(&d, in->data.f, f->data.f, bias ? bias->data.f : nullptr,
+                                             out->data.f, lce_b200_get_stream()));
+  else
+    B_CAPI(c, lce_b200_f32_conv2d(&d, in->data.f, f->data.f, bias ? bias->data.f : nullptr,
+                                  out->data.f, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ------------------------------ FULLY_CONNECTED ------------------------------ //
+TfLiteStatus FcPrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* w = T(c, n->inputs, 1);
+  B_ENSURE(c, in && w && w->dims->size == 2, "FULLY_CONNECTED: weights must be [out, in]");
+  const int k = w->dims->data[1];
+  B_ENSURE(c, k > 0 && Count(in) % k == 0, "FULLY_CONNECTED: input size mismatch");
+  return Resize(c, T(c, n->outputs, 0), {static_cast<int>(Count(in) / k), w->dims->data[0]});
+}
+TfLiteStatus FcInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* w = T(c, n->inputs, 1);
+  const TfLiteTensor* bias = T(c, n->inputs, 2);
+  TfLiteTensor* out = T(c, n->outputs, 0);
+  lce_f32_conv_desc d;
+  memset(&d, 0, sizeof(d));
+  d.batch = static_cast<int>(Count(in) / w->dims->data[1]);
+  d.in_h = d.in_w = d.filter_h = d.filter_w = d.stride_h = d.stride_w = d.dilation_h =
+      d.dilation_w = 1;
+  d.in_c = w->dims->data[1];
+  d.out_c = w->dims->data[0];
+  d.padding = LCE_PADDING_VALID;
+  d.activation = P(n).activation;
+  B_CAPI(c, lce_b200_f32_conv2d(&d, in->data.f, w->data.f, bias ? bias->data.f : nullptr,
+                                out->data.f, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ---------------------------------- pooling ---------------------------------- //
+bool PoolDesc(TfLiteContext* c, TfLiteNode* n, lce_f32_pool_desc* d) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  if (!in || in->dims->size != 4) return false;
+  const BuiltinParams& p = P(n);
+  d->batch = in->dims->data[0]; d->in_h = in->dims->data[1]; d->in_w = in->dims->data[2];
+  d->channels = in->dims->data[3];
+  d->filter_h = p.filter_h; d->filter_w = p.filter_w;
+  d->stride_h = p.stride_h; d->stride_w = p.stride_w;
+  d->padding = p.padding; d->activation = p.activation;
+  return true;
+}
+TfLiteStatus PoolPrepare(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_pool_desc d;
+  B_ENSURE(c, PoolDesc(c, n, &d), "POOL_2D: input must be 4-D");
+  int oh, ow;
+  B_CAPI(c, lce_b200_f32_pool_out_shape(&d, &oh, &ow));
+  return Resize(c, T(c, n->outputs, 0), {d.batch, oh, ow, d.channels});
+}
+template <bool MAX>
+TfLiteStatus PoolInvoke(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_pool_desc d;
+  PoolDesc(c, n, &d);
+  const float* in = T(c, n->inputs, 0)->data.f;
+  float* out = T(c, n->outputs, 0)->data.f;
+  if (MAX) B_CAPI(c, lce_b200_f32_max_pool(&d, in, out, lce_b200_get_stream()));
+  else B_CAPI(c, lce_b200_f32_avg_pool(&d, in, out, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ------------------------------ ADD / MUL / RELU ------------------------------ //
+TfLiteStatus EltPrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  const TfLiteTensor* b = T(c, n->inputs, 1);
+  B_ENSURE(c, a && b, "ADD/MUL: two inputs required");
+  const int64_t na = Count(a), nb = Count(b);
+  B_ENSURE(c, nb > 0 && na % nb == 0 &&
+                  (na == nb || nb == a->dims->data[a->dims->size - 1]),
+           "ADD/MUL: only same-shape or last-dimension broadcast is supported");
+  TfLiteIntArray* dims = LceB200IntArrayCreate(a->dims->size);
+  for (int i = 0; i < a->dims->size; ++i) dims->data[i] = a->dims->data[i];
+  return c->ResizeTensor(c, T(c, n->outputs, 0), dims);
+}
+template <bool MUL>
+TfLiteStatus EltInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  const TfLiteTensor* b = T(c, n->inputs, 1);
+  TfLiteTensor* out = T(c, n->outputs, 0);
+  B_ENSURE(c, OnDevice(b->data.raw), "float builtins need device-resident operands");
+  if (MUL) B_CAPI(c, lce_b200_f32_mul(a->data.f, b->data.f, out->data.f, Count(a), Count(b),
+                                      P(n).activation, lce_b200_get_stream()));
+  else B_CAPI(c, lce_b200_f32_add(a->data.f, b->data.f, out->data.f, Count(a), Count(b),
+                                  P(n).activation, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+TfLiteStatus SameShapePrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  TfLiteIntArray* dims = LceB200IntArrayCreate(a->dims->size);
+  for (int i = 0; i < a->dims->size; ++i) dims->data[i] = a->dims->data[i];
+  return c->ResizeTensor(c, T(c, n->outputs, 0), dims);
+}
+TfLiteStatus ReluInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  B_CAPI(c, lce_b200_f32_activation(a->data.f, T(c, n->outputs, 0)->data.f, Count(a), LCE_ACT_RELU,
+                                    lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ----------------------------------- MEAN ----------------------------------- //
+TfLiteStatus MeanPrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* axes = T(c, n->inputs, 1);
+  B_ENSURE(c, in && in->dims->size == 4, "MEAN: input must be 4-D");
+  // only the global-average-pool form (axes = {1, 2}) is needed by these models
+  bool ok = axes && axes->type == kTfLiteInt32 && Count(axes) == 2 && !OnDevice(axes->data.raw);
+  if (ok) {
+    const int a0 = axes->data.i32[0], a1 = axes->data.i32[1];
+    ok = (a0 == 1 && a1 == 2) || (a0 == 2 && a1 == 1);
+  }
+  B_ENSURE(c, ok, "MEAN: only reduction over axes {1,2} is supported");
+  if (P(n).keep_dims)
+    return Resize(c, T(c, n->outputs, 0), {in->dims->data[0], 1, 1, in->dims->data[3]});
+  return Resize(c, T(c, n->outputs, 0), {in->dims->data[0], in->dims->data[3]});
+}
+TfLiteStatus MeanInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  B_CAPI(c, lce_b200_f32_mean_hw(in->data.f, T(c, n->outputs, 0)->data.f, in->dims->data[0],
+                                 in->dims->data[1], in->dims->data[2], in->dims->data[3],
+                                 lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ---------------------------------- SOFTMAX ---------------------------------- //
+TfLiteStatus SoftmaxInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const int cols = in->dims->data[in->dims->size - 1];
+  B_CAPI(c, lce_b200_f32_softmax(in->data.f, T(c, n->outputs, 0)->data.f,
+                                 cols ? Count(in) / cols : 0, cols, P(n).beta,
+                                 lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ---------------------------------- RESHAPE ---------------------------------- //
+TfLiteStatus ReshapePrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const BuiltinParams& p = P(n);
+  std::vector<int> shape(p.new_shape, p.new_shape + p.n_new_shape);
+  const TfLiteTensor* st = T(c, n->inputs, 1);
+  if (shape.empty() && st && st->type == kTfLiteInt32 && !OnDevice(st->data.raw))
+    shape.assign(st->data.i32, st->data.i32 + Count(st));
+  int64_t known = 1;
+  int wild = -1;
+  for (size_t i = 0; i < shape.size(); ++i) {
+    if (shape[i] == -1) wild = static_cast<int>(i);
+    else known *= shape[i];
+  }
+  if (wild >= 0) shape[wild] = known ? static_cast<int>(Count(in) / known) : 0;
+  int64_t total = 1;
+  for (int d : shape) total *= d;
+  B_ENSURE(c, total == Count(in), "RESHAPE: element count mismatch");
+  TfLiteIntArray* dims = LceB200IntArrayCreate(static_cast<int>(shape.size()));
+  for (size_t i = 0; i < shape.size(); ++i) dims->data[i] = shape[i];
+  return c->ResizeTensor(c, T(c, n->outputs, 0), dims);
+}
+TfLiteStatus ReshapeInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  TfLiteTensor* out = T(c, n->outputs, 0);
+  if (in->bytes && cudaMemcpyAsync(out->data.raw, in->data.raw, in->bytes, cudaMemcpyDeviceToDevice,
+                                   static_cast<cudaStream_t>(lce_b200_get_stream())) != cudaSuccess) {
+    c->ReportError(c, "RESHAPE: device copy failed");
+    return kTfLiteError;
+  }
+  return kTfLiteOk;
+}
+
+}  // namespace
+
+void RegisterBuiltinOps(OpResolver* r) {
+  static TfLiteRegistration conv = {Init, Free, ConvPrepare<false>, ConvInvoke<false>};
+  static TfLiteRegistration dw = {Init, Free, ConvPrepare<true>, ConvInvoke<true>};
+  static TfLiteRegistration fc = {Init, Free, FcPrepare, FcInvoke};
+  static TfLiteRegistration maxp = {Init, Free, PoolPrepare, PoolInvoke<true>};
+  static TfLiteRegistration avgp = {Init, Free, PoolPrepare, PoolInvoke<false>};
+  static TfLiteRegistration add = {Init, Free, EltPrepare, EltInvoke<false>};
+  static TfLiteRegistration mul = {Init, Free, EltPrepare, EltInvoke<true>};
+  static TfLiteRegistration relu = {Init, Free, SameShapePrepare, ReluInvoke};
+  static TfLiteRegistration mean = {Init, Free, MeanPrepare, MeanInvoke};
+  static TfLiteRegistration softmax = {Init, Free, SameShapePrepare, SoftmaxInvoke};
+  static TfLiteRegistration reshape = {Init, Free, ReshapePrepare, ReshapeInvoke};
+  // BuiltinOperator codes, schema.fbs:259-325
+  r->AddBuiltin(3, &conv);
+  r->AddBuiltin(4, &dw);
+  r->AddBuiltin(9, &fc);
+  r->AddBuiltin(17, &maxp);
+  r->AddBuiltin(1, &avgp);
+  r->AddBuiltin(0, &add);
+  r->AddBuiltin(18, &mul);
+  r->AddBuiltin(19, &relu);
+  r->AddBuiltin(40, &mean);
+  r->AddBuiltin(25, &softmax);
+  r->AddBuiltin(22, &reshape);
+}
+
 }  // namespace lce_b200

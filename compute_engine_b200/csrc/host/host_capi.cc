@@ -14,7 +14,9 @@ using lce_b200::Graph;
 using lce_b200::OpResolver;
 
 namespace lce_b200 {
-void RegisterBuiltinOps(OpResolver* resolver);  // builtin_ops.cc (optional)
+void RegisterBuiltinOps(OpResolver* resolver);  // builtin_ops.cc
+bool BuildGraphFromTflite(const uint8_t* data, size_t size, const OpResolver& resolver,
+                          Graph* graph);        // tflite_model.cc
 OpResolver* DefaultResolver() {
   static OpResolver* r = [] {
     auto* res = new OpResolver();
@@ -36,6 +38,22 @@ extern "C" {
 void* lce_host_graph_create(int device_arena) { return new Graph(device_arena != 0); }
 void lce_host_graph_destroy(void* g) { delete static_cast<Graph*>(g); }
 const char* lce_host_last_error(void* g) { return static_cast<Graph*>(g)->last_error().c_str(); }
+
+// FlatBufferModel::BuildFromBuffer + InterpreterBuilder in one call
+// (examples/lce_minimal.cc:31-45). Returns nullptr on failure; *error gets a message
+// valid until the next call on this thread.
+void* lce_host_graph_from_tflite(const uint8_t* data, size_t size, int device_arena,
+                                 const char** error) {
+  static thread_local std::string msg;
+  auto* g = new Graph(device_arena != 0);
+  if (!lce_b200::BuildGraphFromTflite(data, size, *lce_b200::DefaultResolver(), g)) {
+    msg = g->last_error();
+    if (error) *error = msg.c_str();
+    delete g;
+    return nullptr;
+  }
+  return g;
+}
 
 // Make an external registration (e.g. the oracle-backed CPU ops used by the CPU
 // tests) available under `name`.
@@ -80,6 +98,9 @@ int lce_host_resize_input(void* g, int tensor, const int* dims, int ndims) {
 int lce_host_invoke(void* g) { return static_cast<Graph*>(g)->Invoke(); }
 int lce_host_enable_cuda_graph(void* g, int on) {
   return static_cast<Graph*>(g)->EnableCudaGraph(on != 0);
+}
+void lce_host_preserve_all_tensors(void* g, int on) {
+  static_cast<Graph*>(g)->set_preserve_all_tensors(on != 0);
 }
 int lce_host_num_tensors(void* g) { return static_cast<int>(static_cast<Graph*>(g)->num_tensors()); }
 int lce_host_num_nodes(void* g) { return static_cast<int>(static_cast<Graph*>(g)->num_nodes()); }

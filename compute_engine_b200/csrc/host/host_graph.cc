@@ -249,6 +249,9 @@ TfLiteStatus Graph::PlanArena() {
     for (int k = 0; k < nd.temporaries->size; ++k) touch(nd.temporaries->data[k], i);
   }
   for (int t : outputs_) touch(t, n_nodes);
+  if (preserve_all_)
+    for (int t = 0; t < n_t; ++t)
+      if (last[t] >= -1) { first[t] = -1; last[t] = n_nodes; }
   struct Item { int t; size_t bytes; size_t off; };
   std::vector<Item> items;
   for (int t = 0; t < n_t; ++t) {

@@ -72,6 +72,9 @@ class Graph {
   TfLiteStatus Invoke();
   // Capture the node sequence into a CUDA graph and replay it on later Invokes.
   TfLiteStatus EnableCudaGraph(bool on);
+  // Debug aid (TFLite's `preserve_all_tensors`): no arena reuse, so every intermediate
+  // tensor can be read back after Invoke.
+  void set_preserve_all_tensors(bool on) { preserve_all_ = on; allocated_ = false; }
 
   TfLiteTensor* tensor(int i) { return &tensors_[i]; }
   size_t num_tensors() const { return tensors_.size(); }
@@ -112,6 +115,7 @@ class Graph {
   bool allocated_ = false;
   void* stream_ = nullptr;       // cudaStream_t
   bool use_cuda_graph_ = false;
+  bool preserve_all_ = false;
   bool warmed_ = false;          // one eager Invoke has run since the last allocation
   void* graph_exec_ = nullptr;   // cudaGraphExec_t
 };

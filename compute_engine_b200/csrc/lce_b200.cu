@@ -18,10 +18,12 @@
 #include "lce_b200_kernels.cuh"
 
 namespace {
-
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+}  // namespace
 
+// shared with lce_b200_builtins.cu
+namespace lce_b200_internal {
 int fail(const char* fmt, ...) {
   char buf[512];
   va_list ap;
@@ -31,6 +33,17 @@ int fail(const char* fmt, ...) {
   g_err = buf;
   return 1;
 }
+int launch_check(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
+  return 0;
+}
+}  // namespace lce_b200_internal
+using lce_b200_internal::fail;
+using lce_b200_internal::launch_check;
+
+namespace {
 
 #define CUDA_OK(expr)                                                            \
   do {                                                                           \
@@ -41,13 +54,6 @@ int fail(const char* fmt, ...) {
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
-
-int launch_check(const char* what) {
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail("launch of %s failed: %s", what, cudaGetErrorString(e));
-  return 0;
-}
 
 int grid_for(long long work_items, int per_block, int max_blocks = 148 * 16) {
   long long b = (work_items + per_block - 1) / per_block;

@@ -1,0 +1,462 @@
+// lce_b200_builtins.cu -- fp32 TFLite builtins as CUDA kernels (include/
+// lce_b200_builtins.h). These are the callers either side of the binary path in the
+// QuickNet / Bi-RealNet graphs, kept on the device so activations never leave HBM.
+// Semantics follow TFLite's reference kernels (tensorflow/lite/kernels/internal/
+// reference/conv.h:27, depthwiseconv_float.h:25, pooling.h:28,196, add.h,
+// fully_connected.h:29, softmax.h:31, reduce.h); fp32 accumulate with FMA.
+#include <cuda_runtime.h>
+
+#include <cfloat>
+#include <climits>
+#include <cstdint>
+
+#include "lce_b200_builtins.h"
+
+namespace lce_b200_internal {
+int fail(const char* fmt, ...);       // lce_b200.cu
+int launch_check(const char* what);   // lce_b200.cu
+}  // namespace lce_b200_internal
+using lce_b200_internal::fail;
+using lce_b200_internal::launch_check;
+
+namespace {
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  switch (act) {
+    case LCE_ACT_RELU: return fmaxf(x, 0.0f);
+    case LCE_ACT_RELU_N1_TO_1: return fminf(fmaxf(x, -1.0f), 1.0f);
+    case LCE_ACT_RELU6: return fminf(fmaxf(x, 0.0f), 6.0f);
+    default: return x;
+  }
+}
+
+int out_size(int padding, int image, int filter, int stride, int dil) {
+  const int eff = (filter - 1) * dil + 1;
+  if (stride == 0) return 0;
+  if (padding == LCE_PADDING_SAME) return (image + stride - 1) / stride;
+  if (padding == LCE_PADDING_VALID) return (image + stride - eff) / stride;
+  return 0;
+}
+int pad_before(int stride, int dil, int in, int filter, int out) {
+  const int eff = (filter - 1) * dil + 1;
+  int total = (out - 1) * stride + eff - in;
+  if (total < 0) total = 0;
+  return total / 2;
+}
+inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+int grid_for(long long n, int per_block, int max_blocks = 148 * 32) {
+  long long b = (n + per_block - 1) / per_block;
+  if (b < 1) b = 1;
+  if (b > max_blocks) b = max_blocks;
+  return static_cast<int>(b);
+}
+
+struct ConvGeom {
+  int B, H, W, Cin, KH, KW, Cout, sh, sw, dh, dw, ph, pw, OH, OW, act;
+};
+
+// ---- small-K direct convolution: one thread = one output pixel x 16 channels ----
+// (stem 3x3x3->16 and the 16->64 pointwise: K <= 64). Weights for the CTA's channel
+// group sit in shared memory as [K][16].
+constexpr int kDirectMaxK = 64;
+__global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restrict__ in,
+                                                            const float* __restrict__ filter,
+                                                            const float* __restrict__ bias,
+                                                            float* __restrict__ out, ConvGeom g,
+                                                            long long M) {
+  __shared__ float w_s[kDirectMaxK][16];
+  __shared__ float b_s[16];
+  const int K = g.KH * g.KW * g.Cin;
+  const int c0 = blockIdx.y * 16;
+  for (int i = threadIdx.x; i < K * 16; i += blockDim.x) {
+    const int k = i >> 4, c = i & 15;
+    w_s[k][c] = (c0 + c < g.Cout) ? filter[static_cast<size_t>(c0 + c) * K + k] : 0.0f;
+  }
+  if (threadIdx.x < 16)
+    b_s[threadIdx.x] = (bias && c0 + threadIdx.x < g.Cout) ? bias[c0 + threadIdx.x] : 0.0f;
+  __syncthreads();
+  const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (m >= M) return;
+  const int ohw = g.OH * g.OW;
+  const long long b = m / ohw;
+  const int r = static_cast<int>(m - b * ohw);
+  const int oy = r / g.OW, ox = r - oy * g.OW;
+  float acc[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+  int k = 0;
+  for (int fy = 0; fy < g.KH; ++fy) {
+    const int iy = oy * g.sh - g.ph + fy * g.dh;
+    for (int fx = 0; fx < g.KW; ++fx) {
+      const int ix = ox * g.sw - g.pw + fx * g.dw;
+      const bool inside = static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
+                          static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
+      const float* p = in + ((b * g.H + iy) * g.W + ix) * g.Cin;
+      for (int ci = 0; ci < g.Cin; ++ci, ++k) {
+        const float x = inside ? __ldg(p + ci) : 0.0f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) acc[c] = fmaf(x, w_s[k][c], acc[c]);
+      }
+    }
+  }
+  float* o = out + m * g.Cout + c0;
+  if (c0 + 16 <= g.Cout && (g.Cout & 3) == 0) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+      reinterpret_cast<float4*>(o)[q] =
+          make_float4(apply_act(acc[4 * q] + b_s[4 * q], g.act),
+                      apply_act(acc[4 * q + 1] + b_s[4 * q + 1], g.act),
+                      apply_act(acc[4 * q + 2] + b_s[4 * q + 2], g.act),
+                      apply_act(acc[4 * q + 3] + b_s[4 * q + 3], g.act));
+  } else {
+    for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[c] + b_s[c], g.act);
+  }
+}
+
+// ---- general implicit-GEMM convolution: 64x64x16 tiles, 4x4 per thread ----------
+constexpr int kGM = 64, kGN = 64, kGK = 16;
+__global__ void __launch_bounds__(256) conv_gemm_kernel(const float* __restrict__ in,
+                                                        const float* __restrict__ filter,
+                                                        const float* __restrict__ bias,
+                                                        float* __restrict__ out, ConvGeom g,
+                                                        long long M) {
+  __shared__ __align__(16) float A_s[kGK][kGM + 4];
+  __shared__ __align__(16) float B_s[kGK][kGN + 4];
+  __shared__ long long pix_base[kGM];  // offset of (b, iy0, ix0) or -1 for rows past M
+  __shared__ int pix_iy0[kGM], pix_ix0[kGM];
+  const int K = g.KH * g.KW * g.Cin;
+  const int tid = threadIdx.x;
+  const int tx = tid & 15, ty = tid >> 4;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kGM;
+  const int n0 = blockIdx.y * kGN;
+  if (tid < kGM) {
+    const long long m = m0 + tid;
+    if (m < M) {
+      const int ohw = g.OH * g.OW;
+      const long long b = m / ohw;
+      const int r = static_cast<int>(m - b * ohw);
+      const int oy = r / g.OW, ox = r - oy * g.OW;
+      pix_iy0[tid] = oy * g.sh - g.ph;
+      pix_ix0[tid] = ox * g.sw - g.pw;
+      pix_base[tid] = b * g.H * g.W;
+    } else {
+      pix_base[tid] = -1;
+      pix_iy0[tid] = pix_ix0[tid] = 0;
+    }
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  const int lk = tid & 15;   // k within the chunk handled by this thread when loading
+  const int lr = tid >> 4;   // row group: rows lr, lr+16, lr+32, lr+48
+  for (int k0 = 0; k0 < K; k0 += kGK) {
+    const int k = k0 + lk;
+    int fy = 0, fx = 0, ci = 0;
+    const bool k_ok = k < K;
+    if (k_ok) {
+      const int tap = k / g.Cin;
+      ci = k - tap * g.Cin;
+      fy = tap / g.KW;
+      fx = tap - fy * g.KW;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int row = lr + 16 * q;
+      float v = 0.0f;
+      if (k_ok && pix_base[row] >= 0) {
+        const int iy = pix_iy0[row] + fy * g.dh, ix = pix_ix0[row] + fx * g.dw;
+        if (static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
+            static_cast<unsigned>(ix) < static_cast<unsigned>(g.W))
+          v = __ldg(in + (pix_base[row] + static_cast<long long>(iy) * g.W + ix) * g.Cin + ci);
+      }
+      A_s[lk][row] = v;
+      const int n = n0 + row;
+      B_s[lk][row] = (k_ok && n < g.Cout) ? __ldg(filter + static_cast<size_t>(n) * K + k) : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kGK; ++kk) {
+      const float4 a = *reinterpret_cast<const float4*>(&A_s[kk][ty * 4]);
+      const float4 b = *reinterpret_cast<const float4*>(&B_s[kk][tx * 4]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const long long m = m0 + ty * 4 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < g.Cout) out[m * g.Cout + n] = apply_act(acc[i][j] + (bias ? bias[n] : 0.0f), g.act);
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict__ in,
+                                                        const float* __restrict__ filter,
+                                                        const float* __restrict__ bias,
+                                                        float* __restrict__ out, ConvGeom g,
+                                                        long long n) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += stride) {
+    const int c = static_cast<int>(i % g.Cout);
+    long long r = i / g.Cout;
+    const int ox = static_cast<int>(r % g.OW);
+    r /= g.OW;
+    const int oy = static_cast<int>(r % g.OH);
+    const long long b = r / g.OH;
+    float acc = 0.0f;
+    for (int fy = 0; fy < g.KH; ++fy) {
+      const int iy = oy * g.sh - g.ph + fy * g.dh;
+      if (static_cast<unsigned>(iy) >= static_cast<unsigned>(g.H)) continue;
+      for (int fx = 0; fx < g.KW; ++fx) {
+        const int ix = ox * g.sw - g.pw + fx * g.dw;
+        if (static_cast<unsigned>(ix) >= static_cast<unsigned>(g.W)) continue;
+        acc = fmaf(__ldg(in + ((b * g.H + iy) * g.W + ix) * g.Cin + c),
+                   __ldg(filter + (fy * g.KW + fx) * g.Cout + c), acc);
+      }
+    }
+    out[i] = apply_act(acc + (bias ? bias[c] : 0.0f), g.act);
+  }
+}
+
+template <bool MAX>
+__global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
+                                                   float* __restrict__ out, int B, int H, int W,
+                                                   int C, int OH, int OW, int fh, int fw, int sh,
+                                                   int sw, int ph, int pw, int act) {
+  const long long n = static_cast<long long>(B) * OH * OW * C;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += stride) {
+    const int c = static_cast<int>(i % C);
+    long long r = i / C;
+    const int ox = static_cast<int>(r % OW);
+    r /= OW;
+    const int oy = static_cast<int>(r % OH);
+    const long long b = r / OH;
+    const int y0 = oy * sh - ph, x0 = ox * sw - pw;
+    const int ys = max(0, y0), ye = min(H, y0 + fh), xs = max(0, x0), xe = min(W, x0 + fw);
+    float v = MAX ? -FLT_MAX : 0.0f;
+    for (int y = ys; y < ye; ++y)
+      for (int x = xs; x < xe; ++x) {
+        const float e = __ldg(in + ((b * H + y) * W + x) * C + c);
+        v = MAX ? fmaxf(v, e) : v + e;
+      }
+    if (!MAX) v = v / static_cast<float>(max(1, (ye - ys) * (xe - xs)));  // pooling.h:60-78
+    out[i] = apply_act(v, act);
+  }
+}
+
+template <int OP>  // 0 add, 1 mul, 2 activation only
+__global__ void __launch_bounds__(256) eltwise_kernel(const float* __restrict__ a,
+                                                      const float* __restrict__ b,
+                                                      float* __restrict__ out, long long n,
+                                                      long long b_len, int act, int vec_ok) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long t0 = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (vec_ok) {   // same shape, 16-byte aligned, n % 4 == 0: 128-bit path
+    const float4* a4 = reinterpret_cast<const float4*>(a);
+    const float4* b4 = reinterpret_cast<const float4*>(b);
+    float4* o4 = reinterpret_cast<float4*>(out);
+    for (long long i = t0; i < (n >> 2); i += stride) {
+      float4 x = a4[i];
+      if (OP != 2) {
+        const float4 y = b4[i];
+        if (OP == 0) { x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w; }
+        else { x.x *= y.x; x.y *= y.y; x.z *= y.z; x.w *= y.w; }
+      }
+      o4[i] = make_float4(apply_act(x.x, act), apply_act(x.y, act), apply_act(x.z, act),
+                          apply_act(x.w, act));
+    }
+    return;
+  }
+  for (long long i = t0; i < n; i += stride) {
+    float x = a[i];
+    if (OP == 0) x += b[i % b_len];
+    if (OP == 1) x *= b[i % b_len];
+    out[i] = apply_act(x, act);
+  }
+}
+
+// mean over H*W: one thread per (b, c), c fastest => coalesced rows.
+__global__ void __launch_bounds__(256) mean_hw_kernel(const float* __restrict__ in,
+                                                      float* __restrict__ out, int B, int HW,
+                                                      int C) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * C) return;
+  const int b = i / C, c = i - b * C;
+  const float* p = in + static_cast<size_t>(b) * HW * C + c;
+  float s = 0.0f;
+  for (int k = 0; k < HW; ++k) s += p[static_cast<size_t>(k) * C];
+  out[i] = s / static_cast<float>(HW);
+}
+
+// softmax: one warp per row.
+__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ in,
+                                                      float* __restrict__ out, long long rows,
+                                                      int cols, float beta) {
+  const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const float* x = in + row * cols;
+  float mx = -FLT_MAX;
+  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, x[c]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  float sum = 0.0f;
+  for (int c = lane; c < cols; c += 32) sum += expf((x[c] - mx) * beta);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  float* y = out + row * cols;
+  for (int c = lane; c < cols; c += 32) y[c] = expf((x[c] - mx) * beta) / sum;
+}
+
+int make_geom(const lce_f32_conv_desc* d, ConvGeom* g) {
+  if (d->batch < 0 || d->in_h < 1 || d->in_w < 1 || d->in_c < 1 || d->out_c < 1 ||
+      d->filter_h < 1 || d->filter_w < 1 || d->stride_h < 1 || d->stride_w < 1 ||
+      d->dilation_h < 1 || d->dilation_w < 1)
+    return fail("f32 conv: bad parameters");
+  g->B = d->batch; g->H = d->in_h; g->W = d->in_w; g->Cin = d->in_c;
+  g->KH = d->filter_h; g->KW = d->filter_w; g->Cout = d->out_c;
+  g->sh = d->stride_h; g->sw = d->stride_w; g->dh = d->dilation_h; g->dw = d->dilation_w;
+  g->OH = out_size(d->padding, d->in_h, d->filter_h, d->stride_h, d->dilation_h);
+  g->OW = out_size(d->padding, d->in_w, d->filter_w, d->stride_w, d->dilation_w);
+  g->ph = pad_before(d->stride_h, d->dilation_h, d->in_h, d->filter_h, g->OH);
+  g->pw = pad_before(d->stride_w, d->dilation_w, d->in_w, d->filter_w, g->OW);
+  g->act = d->activation;
+  if (g->OH < 0) g->OH = 0;
+  if (g->OW < 0) g->OW = 0;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lce_b200_f32_conv_out_shape(const lce_f32_conv_desc* d, int* out_h, int* out_w) {
+  ConvGeom g;
+  if (make_geom(d, &g)) return 1;
+  *out_h = g.OH;
+  *out_w = g.OW;
+  return 0;
+}
+
+int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float* filter,
+                        const float* bias, float* out, void* stream) {
+  ConvGeom g;
+  if (make_geom(d, &g)) return 1;
+  const long long M = static_cast<long long>(g.B) * g.OH * g.OW;
+  if (M == 0) return 0;
+  const int K = g.KH * g.KW * g.Cin;
+  if (K <= kDirectMaxK) {
+    dim3 grid(static_cast<unsigned>((M + 255) / 256), (g.Cout + 15) / 16);
+    conv_direct16_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, M);
+    return launch_check("conv_direct16_kernel");
+  }
+  dim3 grid(static_cast<unsigned>((M + kGM - 1) / kGM), (g.Cout + kGN - 1) / kGN);
+  conv_gemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, M);
+  return launch_check("conv_gemm_kernel");
+}
+
+int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in,
+                                  const float* filter, const float* bias, float* out,
+                                  void* stream) {
+  ConvGeom g;
+  if (make_geom(d, &g)) return 1;
+  if (d->out_c != d->in_c) return fail("depthwise conv: depth_multiplier must be 1");
+  const long long n = static_cast<long long>(g.B) * g.OH * g.OW * g.Cout;
+  if (n == 0) return 0;
+  depthwise_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, n);
+  return launch_check("depthwise_kernel");
+}
+
+int lce_b200_f32_pool_out_shape(const lce_f32_pool_desc* d, int* out_h, int* out_w) {
+  if (d->filter_h < 1 || d->filter_w < 1 || d->stride_h < 1 || d->stride_w < 1)
+    return fail("pool: bad parameters");
+  *out_h = out_size(d->padding, d->in_h, d->filter_h, d->stride_h, 1);
+  *out_w = out_size(d->padding, d->in_w, d->filter_w, d->stride_w, 1);
+  return 0;
+}
+
+static int run_pool(bool is_max, const lce_f32_pool_desc* d, const float* in, float* out,
+                    void* stream) {
+  int oh, ow;
+  if (lce_b200_f32_pool_out_shape(d, &oh, &ow)) return 1;
+  const long long n = static_cast<long long>(d->batch) * oh * ow * d->channels;
+  if (n <= 0) return 0;
+  const int ph = pad_before(d->stride_h, 1, d->in_h, d->filter_h, oh);
+  const int pw = pad_before(d->stride_w, 1, d->in_w, d->filter_w, ow);
+  if (is_max)
+    pool_kernel<true><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        in, out, d->batch, d->in_h, d->in_w, d->channels, oh, ow, d->filter_h, d->filter_w,
+        d->stride_h, d->stride_w, ph, pw, d->activation);
+  else
+    pool_kernel<false><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
+        in, out, d->batch, d->in_h, d->in_w, d->channels, oh, ow, d->filter_h, d->filter_w,
+        d->stride_h, d->stride_w, ph, pw, d->activation);
+  return launch_check("pool_kernel");
+}
+int lce_b200_f32_max_pool(const lce_f32_pool_desc* d, const float* in, float* out, void* s) {
+  return run_pool(true, d, in, out, s);
+}
+int lce_b200_f32_avg_pool(const lce_f32_pool_desc* d, const float* in, float* out, void* s) {
+  return run_pool(false, d, in, out, s);
+}
+
+static bool vec4_ok(const void* a, const void* b, const void* o, int64_t n, int64_t b_len) {
+  return b_len == n && (n & 3) == 0 && !((uintptr_t)a & 15) && !((uintptr_t)b & 15) &&
+         !((uintptr_t)o & 15);
+}
+int lce_b200_f32_add(const float* a, const float* b, float* out, int64_t n, int64_t b_len,
+                     int act, void* stream) {
+  if (n <= 0) return 0;
+  if (b_len <= 0 || n % b_len) return fail("add: operand shapes do not broadcast");
+  eltwise_kernel<0><<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(
+      a, b, out, n, b_len, act, vec4_ok(a, b, out, n, b_len));
+  return launch_check("eltwise_kernel<add>");
+}
+int lce_b200_f32_mul(const float* a, const float* b, float* out, int64_t n, int64_t b_len,
+                     int act, void* stream) {
+  if (n <= 0) return 0;
+  if (b_len <= 0 || n % b_len) return fail("mul: operand shapes do not broadcast");
+  eltwise_kernel<1><<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(
+      a, b, out, n, b_len, act, vec4_ok(a, b, out, n, b_len));
+  return launch_check("eltwise_kernel<mul>");
+}
+int lce_b200_f32_activation(const float* in, float* out, int64_t n, int act, void* stream) {
+  if (n <= 0) return 0;
+  eltwise_kernel<2><<<grid_for(n / 4 + 1, 256), 256, 0, as_stream(stream)>>>(
+      in, in, out, n, n, act, vec4_ok(in, in, out, n, n));
+  return launch_check("eltwise_kernel<act>");
+}
+
+int lce_b200_f32_mean_hw(const float* in, float* out, int batch, int h, int w, int c,
+                         void* stream) {
+  if (batch <= 0 || c <= 0) return 0;
+  if (h * w <= 0) return fail("mean: empty spatial extent");
+  mean_hw_kernel<<<(batch * c + 255) / 256, 256, 0, as_stream(stream)>>>(in, out, batch, h * w, c);
+  return launch_check("mean_hw_kernel");
+}
+
+int lce_b200_f32_softmax(const float* in, float* out, int64_t rows, int cols, float beta,
+                         void* stream) {
+  if (rows <= 0 || cols <= 0) return 0;
+  const long long threads = rows * 32;
+  softmax_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
+      in, out, rows, cols, beta);
+  return launch_check("softmax_kernel");
+}
+
+}  // extern "C"

@@ -163,6 +163,25 @@ class HostGraph:
     def enable_cuda_graph(self, on=True):
         self._check(lib().lce_host_enable_cuda_graph(self._g, 1 if on else 0), "EnableCudaGraph")
 
+    def preserve_all_tensors(self, on=True):
+        lib().lce_host_preserve_all_tensors(self._g, 1 if on else 0)
+
+    @classmethod
+    def from_tflite(cls, model_bytes: bytes, device_arena=True):
+        L = lib()
+        L.lce_host_graph_from_tflite.restype = C.c_void_p
+        err = C.c_char_p()
+        buf = (C.c_uint8 * len(model_bytes)).from_buffer_copy(model_bytes)
+        h = L.lce_host_graph_from_tflite(buf, C.c_size_t(len(model_bytes)),
+                                         1 if device_arena else 0, C.byref(err))
+        if not h:
+            raise HostError((err.value or b'').decode())
+        g = cls.__new__(cls)
+        g._g = C.c_void_p(h)
+        g.device_arena = device_arena
+        g._keep = []
+        return g
+
     def shape(self, t):
         n = lib().lce_host_tensor_ndims(self._g, t)
         return tuple(lib().lce_host_tensor_dim(self._g, t, i) for i in range(n))

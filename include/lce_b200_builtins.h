@@ -1,0 +1,68 @@
+/*
+ * lce_b200_builtins.h -- C-ABI of the float TFLite builtins the three model
+ * families (QuickNet, QuickNetLarge, Bi-RealNet-18) use AROUND the binary path
+ * (SURVEY 8f-1). In the reference these come from stock TFLite
+ * (tensorflow/lite/kernels/internal/reference/{conv.h:27, depthwiseconv_float.h:25,
+ * pooling.h:28,196, add.h, fully_connected.h:29, softmax.h:31, reduce.h}); here they
+ * are plain fp32 CUDA kernels so the graph never leaves HBM between binary layers.
+ * They are callers of the hot path, not part of it: no tensor cores, no tuning
+ * beyond coalescing. All tensors NHWC fp32, device pointers, async on `stream`.
+ */
+#ifndef LCE_B200_BUILTINS_H_
+#define LCE_B200_BUILTINS_H_
+
+#include <stdint.h>
+
+#include "lce_b200_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct lce_f32_conv_desc {
+  int32_t batch, in_h, in_w, in_c;
+  int32_t filter_h, filter_w, out_c; /* filter OHWI [out_c, fh, fw, in_c] */
+  int32_t stride_h, stride_w, dilation_h, dilation_w;
+  int32_t padding;    /* LCE_PADDING_* (zero padding) */
+  int32_t activation; /* LCE_ACT_* */
+} lce_f32_conv_desc;
+
+typedef struct lce_f32_pool_desc {
+  int32_t batch, in_h, in_w, channels;
+  int32_t filter_h, filter_w, stride_h, stride_w;
+  int32_t padding;
+  int32_t activation;
+} lce_f32_pool_desc;
+
+/* out = act(conv(in, filter) + bias); bias may be NULL. Also used for
+ * FULLY_CONNECTED (1x1 conv on a [B,1,1,K] view). */
+int lce_b200_f32_conv_out_shape(const lce_f32_conv_desc* d, int* out_h, int* out_w);
+int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in_dev, const float* filter_dev,
+                        const float* bias_dev, float* out_dev, void* stream);
+/* depth_multiplier 1; filter [1, fh, fw, C]; d->out_c == d->in_c */
+int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in_dev,
+                                  const float* filter_dev, const float* bias_dev,
+                                  float* out_dev, void* stream);
+int lce_b200_f32_pool_out_shape(const lce_f32_pool_desc* d, int* out_h, int* out_w);
+int lce_b200_f32_max_pool(const lce_f32_pool_desc* d, const float* in_dev, float* out_dev,
+                          void* stream);
+int lce_b200_f32_avg_pool(const lce_f32_pool_desc* d, const float* in_dev, float* out_dev,
+                          void* stream);
+/* out[i] = act(a[i] (op) b[i % b_len]); b_len == n (same shape) or the last dim. */
+int lce_b200_f32_add(const float* a_dev, const float* b_dev, float* out_dev, int64_t n,
+                     int64_t b_len, int activation, void* stream);
+int lce_b200_f32_mul(const float* a_dev, const float* b_dev, float* out_dev, int64_t n,
+                     int64_t b_len, int activation, void* stream);
+int lce_b200_f32_activation(const float* in_dev, float* out_dev, int64_t n, int activation,
+                            void* stream);
+/* mean over H and W: [B,H,W,C] -> [B,C] */
+int lce_b200_f32_mean_hw(const float* in_dev, float* out_dev, int batch, int h, int w, int c,
+                         void* stream);
+/* softmax over the last dim: exp(beta*(x - max)) / sum */
+int lce_b200_f32_softmax(const float* in_dev, float* out_dev, int64_t rows, int cols, float beta,
+                         void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

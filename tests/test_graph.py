@@ -1,0 +1,185 @@
+"""Graph-host tests on synthesised `.tflite` models (the three model families of
+BASELINE.json; topology from the public descriptions, random weights).
+
+CPU: the flatbuffer writer against an independent pure-Python reader; the C++ reader
+against that reader (and against TFLite's own fixtures when /root/reference is
+present); shape inference / resize of every op through prepare.
+GPU: whole graphs through the device-arena host; every LCE custom op is checked BIT
+EXACT against the oracle on the tensors the device itself produced (op-by-op parity),
+the float builtins against a PyTorch fp32 CPU reference within a stated tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import lce_testlib as L
+import tflite_ref as R
+from compute_engine_b200 import host as H
+from compute_engine_b200 import zoo
+
+TF_TESTDATA = "/root/reference/third_party/tensorflow/tensorflow/lite/testdata"
+
+
+@pytest.fixture(scope="module")
+def quicknet_small():
+    return zoo.quicknet(batch=1, image=64, seed=3)
+
+
+def test_writer_roundtrips_through_independent_reader(quicknet_small):
+    m = R.parse(quicknet_small)
+    assert m["version"] == 3 and m["description"] == "QuickNet"
+    kinds = [(o["code"], o["custom"]) for o in m["ops"]]
+    assert kinds.count((32, "LceBconv2d")) == 16 and kinds.count((32, "LceQuantize")) == 16
+    assert kinds.count((0, "")) == 16            # residual ADDs
+    assert kinds.count((3, "")) == 5             # stem conv, stem pointwise, 3 transitions
+    assert kinds.count((4, "")) == 4             # stem depthwise + 3 blur-pools
+    assert m["tensors"][m["inputs"][0]]["shape"] == (1, 64, 64, 3)
+    assert m["tensors"][m["outputs"][0]]["shape"] == (1, 1000)
+    bconvs = [o for o in m["ops"] if o["custom"] == "LceBconv2d"]
+    a = R._flex_ints(bconvs[0]["custom_options"])
+    assert a == {"channels_in": 64, "dilation_height_factor": 1, "dilation_width_factor": 1,
+                 "fused_activation_function": 1, "pad_values": 1, "padding": 0,
+                 "stride_height": 1, "stride_width": 1}
+    assert bconvs[0]["inputs"][4] == -1          # optional thresholds absent
+    filt = m["tensors"][bconvs[-1]["inputs"][1]]
+    assert filt["shape"] == (512, 3, 3, 16) and filt["dtype"] == np.int32
+    # buffers are 16-byte aligned inside the file (schema.fbs:1562)
+    off = quicknet_small.find(filt["data"].tobytes()[:64])
+    assert off > 0 and off % 16 == 0
+
+
+def test_cpp_reader_matches_python_reader(quicknet_small):
+    m = R.parse(quicknet_small)
+    g = H.HostGraph.from_tflite(quicknet_small, device_arena=False)
+    assert g.num_nodes() == len(m["ops"])
+    assert H.lib().lce_host_num_tensors(g._g) == len(m["tensors"])
+    g.allocate_tensors()                         # every prepare runs on the CPU
+    for i, t in enumerate(m["tensors"]):
+        assert g.shape(i) == t["shape"], (i, t["name"])
+        assert g.dtype(i) == t["dtype"]
+    assert [g.shape(t) for t in g.outputs()] == [(1, 1000)]
+    # batch is pinned to 1 by the converter: resizing re-prepares every op
+    g.resize_input(g.inputs()[0], (5, 64, 64, 3))
+    g.allocate_tensors()
+    assert [g.shape(t) for t in g.outputs()] == [(5, 1000)]
+    g.close()
+
+
+def test_all_three_families_build_and_prepare():
+    for name, fn, n_bconv in (("quicknet", zoo.quicknet, 16),
+                              ("quicknet_large", zoo.quicknet_large, 32),
+                              ("birealnet18", zoo.birealnet18, 16)):
+        blob = fn(batch=2)
+        m = R.parse(blob)
+        assert sum(o["custom"] == "LceBconv2d" for o in m["ops"]) == n_bconv
+        g = H.HostGraph.from_tflite(blob, device_arena=False)
+        g.allocate_tensors()
+        assert [g.shape(t) for t in g.outputs()] == [(2, 1000)], name
+        g.close()
+
+
+def test_unknown_custom_op_is_reported():
+    from compute_engine_b200.tflite_writer import TFLiteModel
+    m = TFLiteModel()
+    a = m.add_tensor("a", (1, 4))
+    b = m.add_tensor("b", (1, 4))
+    m.add_op("NotAnLceOp", [a], [b], custom_options=b"")
+    m.inputs, m.outputs = [a], [b]
+    with pytest.raises(H.HostError, match="unresolved custom op: NotAnLceOp"):
+        H.HostGraph.from_tflite(m.serialize(), device_arena=False)
+    with pytest.raises(H.HostError, match="not a TFL3 flatbuffer"):
+        H.HostGraph.from_tflite(b"garbage-bytes-here", device_arena=False)
+
+
+@pytest.mark.skipif(not os.path.isdir(TF_TESTDATA), reason="TFLite fixtures not on this box")
+def test_readers_on_tflite_own_fixtures():
+    for name, n_ops in (("add.bin", 2), ("multi_add.bin", 3)):
+        blob = open(os.path.join(TF_TESTDATA, name), "rb").read()
+        m = R.parse(blob)
+        assert len(m["ops"]) == n_ops, name
+        g = H.HostGraph.from_tflite(blob, device_arena=False)
+        assert g.num_nodes() == n_ops
+        for i, t in enumerate(m["tensors"]):
+            assert g.shape(i) == t["shape"]
+        g.close()
+    blob = open(os.path.join(TF_TESTDATA, "conv_huge_im2col.bin"), "rb").read()
+    assert [o["code"] for o in R.parse(blob)["ops"]] == [2, 3, 0]     # CONCATENATION, CONV_2D, ADD
+    with pytest.raises(H.HostError, match="builtin operator 2 is not supported"):
+        H.HostGraph.from_tflite(blob, device_arena=False)
+    blob = open(os.path.join(TF_TESTDATA, "custom_sinh.bin"), "rb").read()
+    assert R.parse(blob)["ops"][0]["custom"] == "Sinh"
+    with pytest.raises(H.HostError, match="unresolved custom op: Sinh"):
+        H.HostGraph.from_tflite(blob, device_arena=False)
+
+
+# ------------------------------- GPU ------------------------------------- #
+def _check_graph_on_gpu(blob, batch, image, seed, final_atol):
+    m = R.parse(blob)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((batch, image, image, 3)).astype(np.float32)
+    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    g.preserve_all_tensors(True)
+    g.resize_input(g.inputs()[0], x.shape)
+    g.allocate_tensors()
+    g.write(g.inputs()[0], x)
+    g.invoke()
+    want_out, _ = R.run(m, [x])
+    got_out = g.read(g.outputs()[0])
+    # (1) op-by-op: each LCE op, fed with the DEVICE's own input tensor, is bit exact
+    n_lce = 0
+    for op in m["ops"]:
+        if op["code"] != 32:
+            continue
+        sub = {"tensors": m["tensors"], "ops": [op], "inputs": [op["inputs"][0]],
+               "outputs": [op["outputs"][0]]}
+        dev_in = g.read(op["inputs"][0])
+        want, _ = R.run(sub, [dev_in])
+        got = g.read(op["outputs"][0])
+        assert got.shape == want[0].shape
+        assert np.array_equal(got.view(np.uint8), want[0].view(np.uint8)), op["custom"]
+        n_lce += 1
+    # (2) float builtins vs the torch fp32 CPU reference, op by op on device inputs
+    for op in m["ops"]:
+        if op["code"] == 32:
+            continue
+        act_inputs = [i for i in op["inputs"] if i >= 0 and m["tensors"][i]["data"] is None]
+        sub = {"tensors": m["tensors"], "ops": [op], "inputs": act_inputs,
+               "outputs": [op["outputs"][0]]}
+        want, _ = R.run(sub, [g.read(i) for i in act_inputs])
+        got = g.read(op["outputs"][0])
+        scale = max(1.0, float(np.abs(want[0]).max()))
+        assert np.allclose(got, want[0], rtol=1e-4, atol=1e-5 * scale), (op["code"], np.abs(got - want[0]).max())
+    # (3) end to end: class probabilities against the CPU graph
+    assert got_out.shape == want_out[0].shape
+    assert np.abs(got_out - want_out[0]).max() <= final_atol
+    assert np.allclose(got_out.sum(-1), 1.0, atol=1e-4)
+    g.close()
+    return n_lce
+
+
+@pytest.mark.gpu
+def test_gpu_quicknet_graph_parity():
+    assert _check_graph_on_gpu(zoo.quicknet(batch=1, image=64, seed=5), 3, 64, 0, 2e-4) == 32
+
+
+@pytest.mark.gpu
+def test_gpu_birealnet18_graph_parity():
+    assert _check_graph_on_gpu(zoo.birealnet18(batch=1, image=64, seed=6), 2, 64, 1, 2e-4) == 32
+
+
+@pytest.mark.gpu
+def test_gpu_interpreter_predict_true_batching():
+    from compute_engine_b200.interpreter import Interpreter
+    blob = zoo.quicknet(batch=1, image=64, seed=7)
+    it = Interpreter(blob, batch_size=4)
+    assert it.input_shapes == [(1, 64, 64, 3)] and it.output_shapes == [(1, 1000)]
+    assert it.input_types == [np.float32] and it.input_scales == [None]
+    x = np.random.default_rng(2).standard_normal((10, 64, 64, 3)).astype(np.float32)
+    y = it.predict(x)                      # mini-batches 4, 4, 2; CUDA graph re-captured on resize
+    assert y.shape == (10, 1000)
+    y1 = np.concatenate([it.predict(x[i:i + 1]) for i in range(10)])   # the reference's batch-1 loop
+    assert np.allclose(y, y1, atol=1e-6)
+    want, _ = R.run(R.parse(blob), [x])
+    assert np.abs(y - want[0]).max() < 2e-4
+    it.close()
