@@ -99,6 +99,25 @@ int lce_host_invoke(void* g) { return static_cast<Graph*>(g)->Invoke(); }
 int lce_host_enable_cuda_graph(void* g, int on) {
   return static_cast<Graph*>(g)->EnableCudaGraph(on != 0);
 }
+void lce_host_enable_profiling(void* g, int on) { static_cast<Graph*>(g)->EnableProfiling(on != 0); }
+void lce_host_reset_profile(void* g) { static_cast<Graph*>(g)->ResetProfile(); }
+double lce_host_node_time_ms(void* g, int node) { return static_cast<Graph*>(g)->NodeTimeMs(node); }
+const char* lce_host_node_name(void* g, int node) {
+  return static_cast<Graph*>(g)->node(node).name.c_str();
+}
+int lce_host_node_num_inputs(void* g, int node) {
+  return static_cast<Graph*>(g)->node(node).node.inputs->size;
+}
+int lce_host_node_input(void* g, int node, int k) {
+  return static_cast<Graph*>(g)->node(node).node.inputs->data[k];
+}
+int lce_host_node_output(void* g, int node, int k) {
+  return static_cast<Graph*>(g)->node(node).node.outputs->data[k];
+}
+int lce_host_synchronize(void* g) { return static_cast<Graph*>(g)->Synchronize(); }
+int lce_host_tensor_read_async(void* g, int i, void* dst, size_t bytes) {
+  return static_cast<Graph*>(g)->ReadTensorAsync(i, dst, bytes);
+}
 void lce_host_preserve_all_tensors(void* g, int on) {
   static_cast<Graph*>(g)->set_preserve_all_tensors(on != 0);
 }

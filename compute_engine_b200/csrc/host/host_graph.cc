@@ -343,11 +343,27 @@ TfLiteStatus Graph::EnableCudaGraph(bool on) {
 TfLiteStatus Graph::Invoke() {
   if (!allocated_ && AllocateTensors() != kTfLiteOk) return kTfLiteError;
   lce_b200_set_stream(stream_);  // nullptr (legacy default stream) for a host arena
+  const bool prof = profiling_ && device_arena_ && !use_cuda_graph_;
+  if (prof && node_events_.size() != nodes_.size()) {
+    node_events_.assign(nodes_.size(), {});
+    node_ms_.assign(nodes_.size(), 0.0);
+  }
   auto run_nodes = [&]() -> TfLiteStatus {
-    for (auto& n : nodes_) {
+    for (size_t i = 0; i < nodes_.size(); ++i) {
+      auto& n = nodes_[i];
+      cudaEvent_t e0 = nullptr, e1 = nullptr;
+      if (prof) {
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaEventRecord(e0, static_cast<cudaStream_t>(stream_));
+      }
       if (n->registration->invoke(&ctx_, &n->node) != kTfLiteOk) {
         if (error_.empty()) error_ = "invoke failed for node " + n->name;
         return kTfLiteError;
+      }
+      if (prof) {
+        cudaEventRecord(e1, static_cast<cudaStream_t>(stream_));
+        node_events_[i].emplace_back(e0, e1);
       }
     }
     return kTfLiteOk;
@@ -388,6 +404,53 @@ TfLiteStatus Graph::Invoke() {
   return kTfLiteOk;
 }
 
+void Graph::ResetProfile() {
+  for (auto& v : node_events_)
+    for (auto& p : v) {
+      cudaEventDestroy(static_cast<cudaEvent_t>(p.first));
+      cudaEventDestroy(static_cast<cudaEvent_t>(p.second));
+    }
+  node_events_.assign(nodes_.size(), {});
+  node_ms_.assign(nodes_.size(), 0.0);
+}
+
+double Graph::NodeTimeMs(size_t node) {
+  if (node >= node_events_.size()) return 0.0;
+  if (stream_) cudaStreamSynchronize(static_cast<cudaStream_t>(stream_));
+  for (auto& p : node_events_[node]) {
+    float ms = 0.f;
+    if (cudaEventElapsedTime(&ms, static_cast<cudaEvent_t>(p.first),
+                             static_cast<cudaEvent_t>(p.second)) == cudaSuccess)
+      node_ms_[node] += ms;
+    cudaEventDestroy(static_cast<cudaEvent_t>(p.first));
+    cudaEventDestroy(static_cast<cudaEvent_t>(p.second));
+  }
+  node_events_[node].clear();
+  return node_ms_[node];
+}
+
+TfLiteStatus Graph::Synchronize() {
+  if (device_arena_ && cudaStreamSynchronize(static_cast<cudaStream_t>(stream_)) != cudaSuccess) {
+    error_ = std::string("stream synchronize failed: ") + cudaGetErrorString(cudaGetLastError());
+    return kTfLiteError;
+  }
+  return kTfLiteOk;
+}
+
+TfLiteStatus Graph::ReadTensorAsync(int i, void* dst, size_t bytes) {
+  TfLiteTensor& t = tensors_[i];
+  if (bytes > t.bytes || !t.data.raw || !device_arena_) {
+    error_ = "ReadTensorAsync: size mismatch, unallocated tensor or host arena";
+    return kTfLiteError;
+  }
+  if (cudaMemcpyAsync(dst, t.data.raw, bytes, cudaMemcpyDefault,
+                      static_cast<cudaStream_t>(stream_)) != cudaSuccess) {
+    error_ = "ReadTensorAsync: copy failed";
+    return kTfLiteError;
+  }
+  return kTfLiteOk;
+}
+
 TfLiteStatus Graph::WriteTensor(int i, const void* src, size_t bytes) {
   TfLiteTensor& t = tensors_[i];
   if (bytes > t.bytes || !t.data.raw) {
@@ -396,7 +459,7 @@ TfLiteStatus Graph::WriteTensor(int i, const void* src, size_t bytes) {
   }
   if (device_arena_ && t.allocation_type == kTfLiteArenaRw) {
     cudaStream_t s = static_cast<cudaStream_t>(stream_);
-    if (cudaMemcpyAsync(t.data.raw, src, bytes, cudaMemcpyHostToDevice, s) != cudaSuccess) {
+    if (cudaMemcpyAsync(t.data.raw, src, bytes, cudaMemcpyDefault, s) != cudaSuccess) {
       error_ = "WriteTensor: H2D copy failed";
       return kTfLiteError;
     }

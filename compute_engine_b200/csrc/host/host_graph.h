@@ -76,12 +76,21 @@ class Graph {
   // tensor can be read back after Invoke.
   void set_preserve_all_tensors(bool on) { preserve_all_ = on; allocated_ = false; }
 
+  // Per-node device timing (eager mode only): CUDA events on the graph's stream
+  // around every node's invoke; times accumulate until ResetProfile().
+  void EnableProfiling(bool on) { profiling_ = on; }
+  void ResetProfile();
+  double NodeTimeMs(size_t node);   // synchronises the stream
+  TfLiteStatus Synchronize();
+
   TfLiteTensor* tensor(int i) { return &tensors_[i]; }
   size_t num_tensors() const { return tensors_.size(); }
   size_t num_nodes() const { return nodes_.size(); }
   const NodeRecord& node(size_t i) const { return *nodes_[i]; }
   TfLiteStatus WriteTensor(int i, const void* host_src, size_t bytes);
   TfLiteStatus ReadTensor(int i, void* host_dst, size_t bytes);
+  // async on the graph's stream; pinned host or device destinations; no synchronise
+  TfLiteStatus ReadTensorAsync(int i, void* dst, size_t bytes);
   const std::string& last_error() const { return error_; }
   void set_error(const std::string& e) { error_ = e; }
   bool device_arena() const { return device_arena_; }
@@ -116,6 +125,9 @@ class Graph {
   void* stream_ = nullptr;       // cudaStream_t
   bool use_cuda_graph_ = false;
   bool preserve_all_ = false;
+  bool profiling_ = false;
+  std::vector<std::vector<std::pair<void*, void*>>> node_events_;  // pending (start, stop)
+  std::vector<double> node_ms_;
   bool warmed_ = false;          // one eager Invoke has run since the last allocation
   void* graph_exec_ = nullptr;   // cudaGraphExec_t
 };

@@ -45,6 +45,8 @@ def lib():
         L.lce_host_arena_bytes.restype = C.c_size_t
         L.lce_host_stream.restype = C.c_void_p
         L.lce_host_tensor_scale.restype = C.c_float
+        L.lce_host_node_time_ms.restype = C.c_double
+        L.lce_host_node_name.restype = C.c_char_p
         for name in ("lce_host_graph_destroy", "lce_host_last_error", "lce_host_allocate_tensors",
                      "lce_host_invoke", "lce_host_num_tensors", "lce_host_num_nodes",
                      "lce_host_arena_bytes", "lce_host_stream", "lce_host_num_inputs",
@@ -162,6 +164,36 @@ class HostGraph:
 
     def enable_cuda_graph(self, on=True):
         self._check(lib().lce_host_enable_cuda_graph(self._g, 1 if on else 0), "EnableCudaGraph")
+
+    # ---- profiling / async IO (bench.py) ----
+    def enable_profiling(self, on=True):
+        lib().lce_host_enable_profiling(self._g, 1 if on else 0)
+
+    def reset_profile(self):
+        lib().lce_host_reset_profile(self._g)
+
+    def node_times_ms(self):
+        return [lib().lce_host_node_time_ms(self._g, i) for i in range(self.num_nodes())]
+
+    def node_name(self, i):
+        return lib().lce_host_node_name(self._g, i).decode()
+
+    def node_io(self, i):
+        n = lib().lce_host_node_num_inputs(self._g, i)
+        return ([lib().lce_host_node_input(self._g, i, k) for k in range(n)],
+                [lib().lce_host_node_output(self._g, i, 0)])
+
+    def synchronize(self):
+        self._check(lib().lce_host_synchronize(self._g), "Synchronize")
+
+    def write_ptr(self, t, ptr, nbytes):
+        """Async copy from a raw (pinned host or device) pointer on the graph's stream."""
+        self._check(lib().lce_host_tensor_write(self._g, t, C.c_void_p(ptr), C.c_size_t(nbytes)),
+                    "WriteTensor")
+
+    def read_ptr_async(self, t, ptr, nbytes):
+        self._check(lib().lce_host_tensor_read_async(self._g, t, C.c_void_p(ptr),
+                                                     C.c_size_t(nbytes)), "ReadTensorAsync")
 
     def preserve_all_tensors(self, on=True):
         lib().lce_host_preserve_all_tensors(self._g, 1 if on else 0)

@@ -91,7 +91,7 @@ def parse(model_bytes: bytes):
         data = buffers[t.scalar(2, "I")]
         shape = tuple(t.vector(0, "i"))
         tensors.append({"shape": shape, "dtype": dtype, "name": t.string(3),
-                        "data": np.frombuffer(data, dtype).reshape(shape) if data else None,
+                        "data": np.frombuffer(data, dtype).reshape(shape).copy() if data else None,
                         "scale": scales[0] if scales else None,
                         "zero_point": zps[0] if zps else 0})
     ops = []
@@ -189,7 +189,7 @@ def _pool(x, o, is_max):
     return _act(y, act).permute(0, 2, 3, 1).contiguous().numpy()
 
 
-def run(model, inputs, threads=8):
+def run(model, inputs, threads=8, lce_impl="oracle", bconv_kind=0):
     """Execute the parsed model on the CPU. `inputs`: list of arrays (any batch)."""
     vals = {}
     for i, t in enumerate(model["tensors"]):
@@ -203,7 +203,7 @@ def run(model, inputs, threads=8):
         code, custom = op["code"], op["custom"]
         if code == 32 and custom == "LceQuantize":
             zp = model["tensors"][op["inputs"][0]]["zero_point"]
-            out = L.quantize(ins[0], zp)
+            out = L.quantize(ins[0], zp, impl=lce_impl)
         elif code == 32 and custom == "LceDequantize":
             ot = model["tensors"][op["outputs"][0]]
             kind = {np.float32: L.T_FLOAT, np.int8: L.T_INT8, np.bool_: L.T_BOOL}[ot["dtype"]]
@@ -221,7 +221,8 @@ def run(model, inputs, threads=8):
                             a["dilation_height_factor"], a["dilation_width_factor"], a["padding"],
                             a["pad_values"], a["fused_activation_function"], out_type,
                             float(ot["scale"] or 1.0), int(ot["zero_point"]))
-            out = L.bconv2d(d, x, filt, ins[2], ins[3], ins[4], threads=threads)
+            out = L.bconv2d(d, x, filt, ins[2], ins[3], ins[4], impl=lce_impl, kind=bconv_kind,
+                            threads=threads)
         elif code == 32 and custom == "LceBMaxPool2d":
             a = _flex_ints(op["custom_options"])
             x = ins[0]
