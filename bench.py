@@ -306,6 +306,7 @@ def graph_workload(args, D):
         D.dist.broadcast(model, src=0)     # packed weights + graph; the only collective
     model_bytes = model.cpu().numpy().tobytes()
     g = H.HostGraph.from_tflite(model_bytes, device_arena=True)
+    fused = 0 if os.environ.get("LCE_NO_FUSION") else g.fuse_residual_blocks()
     t_in, t_out = g.inputs()[0], g.outputs()[0]
     g.resize_input(t_in, (B, 224, 224, 3))
     g.allocate_tensors()
@@ -340,6 +341,11 @@ def graph_workload(args, D):
     prof_ms, _, _ = D.timed(g.invoke, args.steps, sync, gs)
     node_ms = g.node_times_ms()
     g.enable_profiling(False)
+    if os.environ.get("LCE_BENCH_VERBOSE") and D.rank == 0:
+        for i in range(g.num_nodes()):
+            ins, outs = g.node_io(i)
+            print(f"node {i:3d} {g.node_name(i):28s} {node_ms[i] / args.steps:8.4f} ms  "
+                  f"{g.shape(ins[0])} -> {g.shape(outs[0])}", file=sys.stderr)
 
     # ---- (3) e2e: pinned host input -> H2D -> graph -> D2H of the result, every step,
     #      double-buffered so the copy of step i+1 overlaps the compute of step i
@@ -388,11 +394,15 @@ def graph_workload(args, D):
     for i in range(g.num_nodes()):
         name = g.node_name(i)
         by_op[name] = by_op.get(name, 0.0) + node_ms[i]
-        if name != "LceBconv2d":
+        if not name.startswith("LceBconv2d"):
             continue
         ins, outs = g.node_io(i)
         conv_ms += node_ms[i]
         conv_bytes += bconv_alg_bytes(g.shape(ins[0]), g.shape(ins[1]), g.shape(outs[0]))
+        if "+ADD" in name:            # fused shortcut read (+ packed signs written)
+            conv_bytes += int(np.prod(g.shape(outs[0]))) * 4
+        if "+LceQuantize" in name:
+            conv_bytes += int(np.prod(g.shape(outs[0]))) // 8
         conv_words += bconv_word_ops(g.shape(outs[0]), g.shape(ins[1]))
         n_conv += 1
     K = args.steps
@@ -404,6 +414,7 @@ def graph_workload(args, D):
             "by_op_ms_per_step": {k: round(v / K, 4) for k, v in
                                   sorted(by_op.items(), key=lambda kv: -kv[1])},
             "arena_bytes": g.arena_bytes(), "model_bytes": len(model_bytes),
+            "fused_nodes_removed": fused, "graph_nodes": g.num_nodes(),
             "timing_note": "value: CUDA-graph replay; roofline: separate eager pass of the same K "
                            "steps with CUDA events around every node on the graph's stream"}
 
@@ -580,7 +591,8 @@ def main_b200(args):
                            "d2h_bytes_per_step": r["out_bytes"], "ms_per_step": r["e2e_ms"] / K,
                            "note": "pinned host input -> H2D -> graph -> D2H result every step; "
                                    "the copy of step i+1 overlaps the compute of step i"}
-        for k in ("by_op_ms_per_step", "eager_ms_per_step", "arena_bytes", "model_bytes"):
+        for k in ("by_op_ms_per_step", "eager_ms_per_step", "arena_bytes", "model_bytes",
+                  "fused_nodes_removed", "graph_nodes"):
             if k in r:
                 line["config"][k] = r[k]
         if not args.no_cpu_baseline and D.world == 1:

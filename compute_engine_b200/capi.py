@@ -55,7 +55,7 @@ EXPORTS = [
     "lce_b200_quantize", "lce_b200_dequantize", "lce_b200_bmaxpool_out_shape",
     "lce_b200_bmaxpool", "lce_b200_bconv2d_out_shape", "lce_b200_bconv2d_create",
     "lce_b200_bconv2d_set_input_shape", "lce_b200_bconv2d_get_desc",
-    "lce_b200_bconv2d_run", "lce_b200_bconv2d_run_f32", "lce_b200_bconv2d_run_host",
+    "lce_b200_bconv2d_run", "lce_b200_bconv2d_run_fused", "lce_b200_bconv2d_run_f32", "lce_b200_bconv2d_run_host",
     "lce_b200_bconv2d_destroy", "lce_b200_bgemm_create", "lce_b200_bgemm_run",
     "lce_b200_bgemm_destroy", "lce_b200_launch_count",
 ]

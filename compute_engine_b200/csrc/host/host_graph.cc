@@ -1,5 +1,7 @@
 #include "host_graph.h"
 
+#include "builtin_params.h"
+
 #include <cuda_runtime.h>
 
 #include <algorithm>
@@ -293,6 +295,89 @@ TfLiteStatus Graph::PlanArena() {
   }
   for (auto& p : placed) tensors_[p.t].data.raw = static_cast<char*>(arena_) + p.off;
   return kTfLiteOk;
+}
+
+extern "C" TfLiteRegistration* lce_b200_internal_Register_BCONV_2D_FUSED(void);
+
+int Graph::FuseResidualBlocks() {
+  if (!device_arena_) return 0;
+  int removed = 0;
+  auto consumers = [&](int t) {
+    std::vector<size_t> c;
+    for (size_t i = 0; i < nodes_.size(); ++i) {
+      const TfLiteIntArray* in = nodes_[i]->node.inputs;
+      for (int k = 0; k < in->size; ++k)
+        if (in->data[k] == t) { c.push_back(i); break; }
+    }
+    return c;
+  };
+  auto is_graph_output = [&](int t) {
+    return std::find(outputs_.begin(), outputs_.end(), t) != outputs_.end();
+  };
+  for (size_t i = 0; i < nodes_.size(); ++i) {
+    NodeRecord& b = *nodes_[i];
+    if (b.name != "LceBconv2d" || b.initialized || b.node.inputs->size != 5) continue;
+    const int y = b.node.outputs->data[0];
+    if (tensors_[y].type != kTfLiteFloat32 || is_graph_output(y)) continue;
+    std::vector<size_t> cy = consumers(y);
+    if (cy.size() != 1) continue;
+    const size_t ai = cy[0];
+    NodeRecord& a = *nodes_[ai];
+    if (a.name != "builtin:0" || a.node.inputs->size != 2 || ai <= i) continue;  // ADD
+    const int in0 = a.node.inputs->data[0], in1 = a.node.inputs->data[1];
+    if (in0 == in1) continue;
+    const int r = in0 == y ? in1 : in0;
+    if (tensors_[r].type != kTfLiteFloat32 || tensors_[r].allocation_type == kTfLiteMmapRo) continue;
+    // the shortcut must already exist when the bconv runs
+    bool r_ready = std::find(inputs_.begin(), inputs_.end(), r) != inputs_.end();
+    for (size_t k = 0; k < i && !r_ready; ++k)
+      for (int q = 0; q < nodes_[k]->node.outputs->size; ++q)
+        if (nodes_[k]->node.outputs->data[q] == r) r_ready = true;
+    if (!r_ready) continue;
+    const int o = a.node.outputs->data[0];
+    int32_t add_act = 0;
+    if (a.builtin_blob.size() >= sizeof(BuiltinParams))
+      add_act = reinterpret_cast<const BuiltinParams*>(a.builtin_blob.data())->activation;
+    // optional: the LceQuantize that consumes the sum
+    int packed = -1;
+    size_t qi = nodes_.size();
+    for (size_t c : consumers(o)) {
+      NodeRecord& q = *nodes_[c];
+      if (q.name == "LceQuantize" && c > ai && tensors_[o].type == kTfLiteFloat32) {
+        packed = q.node.outputs->data[0];
+        qi = c;
+        break;
+      }
+    }
+    // rewrite node i
+    std::vector<int> ins(b.node.inputs->data, b.node.inputs->data + 5);
+    ins.push_back(r);
+    std::vector<int> outs{o};
+    if (packed >= 0) outs.push_back(packed);
+    LceB200IntArrayFree(b.node.inputs);
+    LceB200IntArrayFree(b.node.outputs);
+    b.node.inputs = MakeDims(ins);
+    b.node.outputs = MakeDims(outs);
+    b.registration = lce_b200_internal_Register_BCONV_2D_FUSED();
+    b.builtin_blob.assign(reinterpret_cast<const uint8_t*>(&add_act),
+                          reinterpret_cast<const uint8_t*>(&add_act) + 4);
+    b.node.builtin_data = b.builtin_blob.data();
+    b.name = packed >= 0 ? "LceBconv2d+ADD+LceQuantize" : "LceBconv2d+ADD";
+    // drop the absorbed nodes (higher index first)
+    auto drop = [&](size_t idx) {
+      NodeRecord& n = *nodes_[idx];
+      LceB200IntArrayFree(n.node.inputs);
+      LceB200IntArrayFree(n.node.outputs);
+      LceB200IntArrayFree(n.node.temporaries);
+      LceB200IntArrayFree(n.node.intermediates);
+      nodes_.erase(nodes_.begin() + idx);
+      ++removed;
+    };
+    if (qi < nodes_.size()) drop(qi);
+    drop(ai);
+  }
+  allocated_ = false;
+  return removed;
 }
 
 TfLiteStatus Graph::AllocateTensors() {

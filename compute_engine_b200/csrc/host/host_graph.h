@@ -66,6 +66,13 @@ class Graph {
   const std::vector<int>& inputs() const { return inputs_; }
   const std::vector<int>& outputs() const { return outputs_; }
 
+  // Graph-level fusion of the converter's residual-block pattern
+  //   LceBconv2d(float out y) -> ADD(y, shortcut) [-> LceQuantize of the sum]
+  // into one node (the bconv epilogue adds the shortcut and emits the packed signs for
+  // the next binary layer). Bit-identical results; y must have no other consumer.
+  // Returns the number of (ADD, LceQuantize) nodes removed. Call before AllocateTensors.
+  int FuseResidualBlocks();
+
   // init (first time) + prepare of every node in order, then arena allocation.
   TfLiteStatus AllocateTensors();
   TfLiteStatus ResizeInputTensor(int tensor, const std::vector<int>& dims);

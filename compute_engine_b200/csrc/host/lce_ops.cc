@@ -200,13 +200,13 @@ void* BconvInit(TfLiteContext* context, const char* buffer, size_t length) {
 
 void BconvFree(TfLiteContext*, void* buffer) { delete static_cast<BconvOpData*>(buffer); }
 
-template <KernelType kernel_type>
+template <KernelType kernel_type, bool FUSED = false>
 TfLiteStatus BconvPrepare(TfLiteContext* context, TfLiteNode* node) {
   auto* op = static_cast<BconvOpData*>(node->user_data);
   if (!op->successfully_initialized) return kTfLiteError;
   lce_bconv2d_desc& d = op->desc;
 
-  LCE_ENSURE(context, node->inputs->size == 5);
+  LCE_ENSURE(context, node->inputs->size == (FUSED ? 6 : 5));
   const TfLiteTensor* input = GetInput(context, node, 0);
   const TfLiteTensor* filter = GetInput(context, node, 1);
   const TfLiteTensor* post_mul = GetInput(context, node, 2);
@@ -296,6 +296,25 @@ TfLiteStatus BconvPrepare(TfLiteContext* context, TfLiteNode* node) {
   output_shape->data[3] =
       output->type == kTfLiteInt32 ? BitpackedSize(d.channels_out) : d.channels_out;
   if (context->ResizeTensor(context, output, output_shape) != kTfLiteOk) return kTfLiteError;
+  if (FUSED) {
+    // graph-level fusion (host_graph.cc::FuseResidualBlocks): input 5 = the shortcut of the
+    // ADD that followed, optional output 1 = the LceQuantize of the sum.
+    const TfLiteTensor* residual = GetInput(context, node, 5);
+    LCE_ENSURE(context, output->type == kTfLiteFloat32 && residual != nullptr);
+    LCE_ENSURE(context, residual->type == kTfLiteFloat32 && NumDims(residual) == 4);
+    LCE_ENSURE(context, Dim(residual, 0) == d.batch && Dim(residual, 1) == out_h &&
+                            Dim(residual, 2) == out_w && Dim(residual, 3) == d.channels_out);
+    if (node->outputs->size > 1) {
+      LCE_ENSURE(context, d.groups == 1);
+      TfLiteIntArray* packed_shape = LceB200IntArrayCreate(4);
+      packed_shape->data[0] = d.batch;
+      packed_shape->data[1] = out_h;
+      packed_shape->data[2] = out_w;
+      packed_shape->data[3] = BitpackedSize(d.channels_out);
+      if (context->ResizeTensor(context, GetOutput(context, node, 1), packed_shape) != kTfLiteOk)
+        return kTfLiteError;
+    }
+  }
 
   // "Prepare could be called multiple times; when the input tensor is resized, we
   // should always re-do the one-time setup" (bconv2d.cc:295-297).
@@ -303,7 +322,47 @@ TfLiteStatus BconvPrepare(TfLiteContext* context, TfLiteNode* node) {
   return kTfLiteOk;
 }
 
+TfLiteStatus BconvEnsurePlan(TfLiteContext* context, TfLiteNode* node);
+
+// Fused node: [in, filter, mul, bias, thr, residual] -> [out, packed_out?]; device arena only.
+TfLiteStatus BconvFusedEval(TfLiteContext* context, TfLiteNode* node) {
+  auto* op = static_cast<BconvOpData*>(node->user_data);
+  if (BconvEnsurePlan(context, node) != kTfLiteOk) return kTfLiteError;
+  const TfLiteTensor* input = GetInput(context, node, 0);
+  const TfLiteTensor* residual = GetInput(context, node, 5);
+  TfLiteTensor* output = GetOutput(context, node, 0);
+  TfLiteTensor* packed = node->outputs->size > 1 ? GetOutput(context, node, 1) : nullptr;
+  int add_act = LCE_ACT_NONE;
+  if (node->builtin_data) add_act = *static_cast<const int32_t*>(node->builtin_data);
+  LCE_ENSURE_MSG(context, OnDevice(input->data.raw) && OnDevice(output->data.raw) &&
+                              OnDevice(residual->data.raw),
+                 "fused LceBconv2d needs a device arena");
+  LCE_ENSURE_CAPI(context,
+                  lce_b200_bconv2d_run_fused(op->plan, input->data.i32, residual->data.f, add_act,
+                                             output->data.f, packed ? packed->data.i32 : nullptr,
+                                             g_stream));
+  return kTfLiteOk;
+}
+
 TfLiteStatus BconvEval(TfLiteContext* context, TfLiteNode* node) {
+  auto* op = static_cast<BconvOpData*>(node->user_data);
+  if (BconvEnsurePlan(context, node) != kTfLiteOk) return kTfLiteError;
+  const TfLiteTensor* input = GetInput(context, node, 0);
+  TfLiteTensor* output = GetOutput(context, node, 0);
+  const TfLiteType ot = output->type;
+  if (ot != kTfLiteFloat32 && ot != kTfLiteInt8 && ot != kTfLiteInt32) return kTfLiteError;
+  return WithDeviceIO(context, &op->staging, input, output,
+                      [&](const void* in_dev, void* out_dev) -> TfLiteStatus {
+                        LCE_ENSURE_CAPI(context,
+                                        lce_b200_bconv2d_run(op->plan,
+                                                             static_cast<const int32_t*>(in_dev),
+                                                             out_dev, g_stream));
+                        return kTfLiteOk;
+                      });
+}
+
+// OneTimeSetup (bconv2d.cc:324-392): build / refresh the plan after a (re)prepare.
+TfLiteStatus BconvEnsurePlan(TfLiteContext* context, TfLiteNode* node) {
   auto* op = static_cast<BconvOpData*>(node->user_data);
   const TfLiteTensor* input = GetInput(context, node, 0);
   const TfLiteTensor* filter = GetInput(context, node, 1);
@@ -314,7 +373,7 @@ TfLiteStatus BconvEval(TfLiteContext* context, TfLiteNode* node) {
   const TfLiteType ot = output->type;
   if (ot != kTfLiteFloat32 && ot != kTfLiteInt8 && ot != kTfLiteInt32) return kTfLiteError;
 
-  if (op->plan_stale) {  // OneTimeSetup (bconv2d.cc:324-392)
+  if (op->plan_stale) {
     if (op->plan && op->plan_filter == filter->data.raw_const) {
       LCE_ENSURE_CAPI(context, lce_b200_bconv2d_set_input_shape(op->plan, op->desc.batch,
                                                                  op->desc.in_h, op->desc.in_w));
@@ -330,14 +389,8 @@ TfLiteStatus BconvEval(TfLiteContext* context, TfLiteNode* node) {
     }
     op->plan_stale = false;
   }
-  return WithDeviceIO(context, &op->staging, input, output,
-                      [&](const void* in_dev, void* out_dev) -> TfLiteStatus {
-                        LCE_ENSURE_CAPI(context,
-                                        lce_b200_bconv2d_run(op->plan,
-                                                             static_cast<const int32_t*>(in_dev),
-                                                             out_dev, g_stream));
-                        return kTfLiteOk;
-                      });
+  (void)input;
+  return kTfLiteOk;
 }
 
 // ------------------------------------------------------------------------- //
@@ -500,6 +553,12 @@ TfLiteStatus BMaxPoolEval(TfLiteContext* context, TfLiteNode* node) {
                       });
 }
 
+TfLiteRegistration* BconvFusedRegistration() {
+  static TfLiteRegistration r = {BconvInit, BconvFree, BconvPrepare<KernelType::kCuda, true>,
+                                 BconvFusedEval};
+  return &r;
+}
+
 template <KernelType kt>
 TfLiteRegistration* BconvRegistration() {
   static TfLiteRegistration r = {BconvInit, BconvFree, BconvPrepare<kt>, BconvEval};
@@ -519,6 +578,9 @@ TfLiteIntArray* LceB200IntArrayCreate(int size) {
 }
 void LceB200IntArrayFree(TfLiteIntArray* a) { free(a); }
 #endif
+
+// host-internal: the fused residual-block node created by Graph::FuseResidualBlocks
+TfLiteRegistration* lce_b200_internal_Register_BCONV_2D_FUSED(void) { return BconvFusedRegistration(); }
 
 void lce_b200_set_stream(void* stream) { g_stream = stream; }
 void* lce_b200_get_stream(void) { return g_stream; }

@@ -459,8 +459,9 @@ static size_t bconv_out_bytes(const lce_b200_bconv2d* plan) {
   }
 }
 
-int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev, void* out_dev,
-                         void* stream) {
+static int bconv_run_impl(lce_b200_bconv2d* plan, const int32_t* in_dev, void* out_dev,
+                          const float* residual, int residual_act, int32_t* packed_out,
+                          void* stream) {
   const lce_bconv2d_desc& d = plan->d;
   const GemmCore& c = plan->core;
   cudaStream_t s = as_stream(stream);
@@ -468,6 +469,7 @@ int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev, void* ou
   memset(&p, 0, sizeof(p));
   p.in = in_dev; p.wt = c.wt; p.out = out_dev;
   p.mul = c.mul; p.bias = c.bias; p.thr = c.thr; p.tap_popc = c.tap_popc;
+  p.residual = residual; p.packed_out = packed_out; p.residual_act = residual_act;
   p.M = static_cast<long long>(d.batch) * plan->out_h * plan->out_w;
   p.H = d.in_h; p.W = d.in_w;
   p.Cw_total = cdiv(d.channels_in, 32);
@@ -493,6 +495,24 @@ int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev, void* ou
   if (d.out_type == LCE_OUT_BITPACKED && !p.bp_fast)
     CUDA_OK(cudaMemsetAsync(out_dev, 0, bconv_out_bytes(plan), s));
   return launch_conv(c, p, s);
+}
+
+int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev, void* out_dev,
+                         void* stream) {
+  return bconv_run_impl(plan, in_dev, out_dev, nullptr, LCE_ACT_NONE, nullptr, stream);
+}
+
+int lce_b200_bconv2d_run_fused(lce_b200_bconv2d* plan, const int32_t* in_dev,
+                               const float* residual_dev, int add_activation, float* out_dev,
+                               int32_t* packed_out_dev, void* stream) {
+  if (plan->d.out_type != LCE_OUT_FLOAT)
+    return fail("bconv2d_run_fused: only float-output plans can take a residual");
+  if (packed_out_dev && plan->d.groups != 1)
+    return fail("bconv2d_run_fused: packed output needs groups == 1");
+  if (residual_dev && (reinterpret_cast<uintptr_t>(residual_dev) & 15u) != 0)
+    return fail("bconv2d_run_fused: residual must be 16-byte aligned");
+  return bconv_run_impl(plan, in_dev, out_dev, residual_dev, add_activation, packed_out_dev,
+                        stream);
 }
 
 int lce_b200_bconv2d_run_f32(lce_b200_bconv2d* plan, const float* in_dev, void* out_dev,

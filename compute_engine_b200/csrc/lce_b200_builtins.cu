@@ -231,6 +231,76 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
   }
 }
 
+// 4 channels per thread (C % 4 == 0): 128-bit loads of inputs, weights and outputs.
+__global__ void __launch_bounds__(256) depthwise_v4_kernel(const float4* __restrict__ in,
+                                                           const float4* __restrict__ filter,
+                                                           const float4* __restrict__ bias,
+                                                           float4* __restrict__ out, ConvGeom g,
+                                                           long long n4) {
+  const int C4 = g.Cout >> 2;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
+       i += stride) {
+    const int c = static_cast<int>(i % C4);
+    long long r = i / C4;
+    const int ox = static_cast<int>(r % g.OW);
+    r /= g.OW;
+    const int oy = static_cast<int>(r % g.OH);
+    const long long b = r / g.OH;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int fy = 0; fy < g.KH; ++fy) {
+      const int iy = oy * g.sh - g.ph + fy * g.dh;
+      if (static_cast<unsigned>(iy) >= static_cast<unsigned>(g.H)) continue;
+      for (int fx = 0; fx < g.KW; ++fx) {
+        const int ix = ox * g.sw - g.pw + fx * g.dw;
+        if (static_cast<unsigned>(ix) >= static_cast<unsigned>(g.W)) continue;
+        const float4 x = __ldg(in + ((b * g.H + iy) * g.W + ix) * C4 + c);
+        const float4 w = __ldg(filter + (fy * g.KW + fx) * C4 + c);
+        acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y);
+        acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
+      }
+    }
+    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (bias) bb = __ldg(bias + c);
+    out[i] = make_float4(apply_act(acc.x + bb.x, g.act), apply_act(acc.y + bb.y, g.act),
+                         apply_act(acc.z + bb.z, g.act), apply_act(acc.w + bb.w, g.act));
+  }
+}
+
+template <bool MAX>
+__global__ void __launch_bounds__(256) pool_v4_kernel(const float4* __restrict__ in,
+                                                      float4* __restrict__ out, int B, int H,
+                                                      int W, int C4, int OH, int OW, int fh, int fw,
+                                                      int sh, int sw, int ph, int pw, int act) {
+  const long long n = static_cast<long long>(B) * OH * OW * C4;
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+       i += stride) {
+    const int c = static_cast<int>(i % C4);
+    long long r = i / C4;
+    const int ox = static_cast<int>(r % OW);
+    r /= OW;
+    const int oy = static_cast<int>(r % OH);
+    const long long b = r / OH;
+    const int y0 = oy * sh - ph, x0 = ox * sw - pw;
+    const int ys = max(0, y0), ye = min(H, y0 + fh), xs = max(0, x0), xe = min(W, x0 + fw);
+    float4 v = MAX ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX)
+                   : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int y = ys; y < ye; ++y)
+      for (int x = xs; x < xe; ++x) {
+        const float4 e = __ldg(in + ((b * H + y) * W + x) * C4 + c);
+        if (MAX) { v.x = fmaxf(v.x, e.x); v.y = fmaxf(v.y, e.y); v.z = fmaxf(v.z, e.z); v.w = fmaxf(v.w, e.w); }
+        else { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+      }
+    if (!MAX) {
+      const float d = static_cast<float>(max(1, (ye - ys) * (xe - xs)));
+      v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
+    }
+    out[i] = make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act),
+                         apply_act(v.w, act));
+  }
+}
+
 template <bool MAX>
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
                                                    float* __restrict__ out, int B, int H, int W,
@@ -378,6 +448,14 @@ int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in,
   if (d->out_c != d->in_c) return fail("depthwise conv: depth_multiplier must be 1");
   const long long n = static_cast<long long>(g.B) * g.OH * g.OW * g.Cout;
   if (n == 0) return 0;
+  const bool a16 = !((uintptr_t)in & 15) && !((uintptr_t)filter & 15) && !((uintptr_t)out & 15) &&
+                   !((uintptr_t)bias & 15);
+  if ((g.Cout & 3) == 0 && a16) {
+    depthwise_v4_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
+        reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g, n / 4);
+    return launch_check("depthwise_v4_kernel");
+  }
   depthwise_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, n);
   return launch_check("depthwise_kernel");
 }
@@ -398,6 +476,20 @@ static int run_pool(bool is_max, const lce_f32_pool_desc* d, const float* in, fl
   if (n <= 0) return 0;
   const int ph = pad_before(d->stride_h, 1, d->in_h, d->filter_h, oh);
   const int pw = pad_before(d->stride_w, 1, d->in_w, d->filter_w, ow);
+  if ((d->channels & 3) == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15)) {
+    const int C4 = d->channels >> 2;
+    if (is_max)
+      pool_v4_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+          reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->batch, d->in_h,
+          d->in_w, C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw,
+          d->activation);
+    else
+      pool_v4_kernel<false><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+          reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->batch, d->in_h,
+          d->in_w, C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw,
+          d->activation);
+    return launch_check("pool_v4_kernel");
+  }
   if (is_max)
     pool_kernel<true><<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(
         in, out, d->batch, d->in_h, d->in_w, d->channels, oh, ow, d->filter_h, d->filter_w,

@@ -40,6 +40,11 @@ struct ConvKParams {
   const float* bias;        // folded bias
   const int32_t* thr;       // thresholds
   const int32_t* tap_popc;  // [cout + BN][taps] popcounts, zero-padding correction; or nullptr
+  // Fused residual-block tail (float output only): out = act(y + residual) -- the TFLite ADD
+  // that follows LceBconv2d -- and packed_out = LceQuantize(out) for the next binary layer.
+  const float* residual;    // [M][cout] or nullptr
+  int32_t* packed_out;      // [M][cw_out] or nullptr
+  int residual_act;         // fused activation of the ADD
   long long M;              // batch * out_h * out_w
   int H, W, Cw_total, Cw_pg, CwV;
   int KH, KW, sh, sw, dh, dw, ph, pw, OH, OW;
@@ -360,19 +365,57 @@ __global__ void __launch_bounds__(kThreads, 2) bconv_kernel(const ConvKParams p)
           if (cofs + j < valid) o[j] = acc[i][j];
       }
     } else if (OUT == LCE_OUT_FLOAT) {
-      if (!row_ok) continue;
       float y[kTN];
 #pragma unroll
       for (int j = 0; j < kTN; ++j)
         y[j] = transform_float(acc[i][j], p.clamp_min, p.clamp_max, mul_r[j], bias_r[j]);
       float* o = static_cast<float*>(p.out) + m * p.cout + c0;
-      if (full && p.vec_store) {
-        reinterpret_cast<float4*>(o)[0] = make_float4(y[0], y[1], y[2], y[3]);
-        reinterpret_cast<float4*>(o)[1] = make_float4(y[4], y[5], y[6], y[7]);
-      } else {
+      if (p.residual != nullptr && row_ok) {
+        const float* r = p.residual + m * p.cout + c0;
+        if (full && p.vec_store) {
+          const float4 r0 = reinterpret_cast<const float4*>(r)[0];
+          const float4 r1 = reinterpret_cast<const float4*>(r)[1];
+          y[0] = __fadd_rn(y[0], r0.x); y[1] = __fadd_rn(y[1], r0.y);
+          y[2] = __fadd_rn(y[2], r0.z); y[3] = __fadd_rn(y[3], r0.w);
+          y[4] = __fadd_rn(y[4], r1.x); y[5] = __fadd_rn(y[5], r1.y);
+          y[6] = __fadd_rn(y[6], r1.z); y[7] = __fadd_rn(y[7], r1.w);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kTN; ++j)
+            if (cofs + j < valid) y[j] = __fadd_rn(y[j], r[j]);
+        }
+        if (p.residual_act != LCE_ACT_NONE) {
+#pragma unroll
+          for (int j = 0; j < kTN; ++j) {
+            if (p.residual_act == LCE_ACT_RELU) y[j] = fmaxf(y[j], 0.0f);
+            else if (p.residual_act == LCE_ACT_RELU6) y[j] = fminf(fmaxf(y[j], 0.0f), 6.0f);
+            else y[j] = fminf(fmaxf(y[j], -1.0f), 1.0f);
+          }
+        }
+      }
+      if (row_ok) {
+        if (full && p.vec_store) {
+          reinterpret_cast<float4*>(o)[0] = make_float4(y[0], y[1], y[2], y[3]);
+          reinterpret_cast<float4*>(o)[1] = make_float4(y[4], y[5], y[6], y[7]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < kTN; ++j)
+            if (cofs + j < valid) o[j] = y[j];
+        }
+      }
+      if (p.packed_out != nullptr) {
+        // LceQuantize of the value just written: bit = value < 0 (bitpack.h:159); the
+        // four lanes holding one word's bytes combine with two shuffles (all lanes run them).
+        uint32_t bits = 0;
 #pragma unroll
         for (int j = 0; j < kTN; ++j)
-          if (cofs + j < valid) o[j] = y[j];
+          if (cofs + j < valid && y[j] < 0.0f) bits |= 1u << j;
+        uint32_t v = bits << (8 * (tn & 3));
+        v |= __shfl_xor_sync(0xffffffffu, v, 1);
+        v |= __shfl_xor_sync(0xffffffffu, v, 2);
+        const int q = tn >> 2;
+        if (row_ok && (tn & 3) == 0 && q * 32 < valid)
+          p.packed_out[m * p.cw_out + (c_tile >> 5) + q] = static_cast<int32_t>(v);
       }
     } else if (OUT == LCE_OUT_INT8) {
       if (!row_ok) continue;

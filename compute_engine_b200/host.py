@@ -165,6 +165,10 @@ class HostGraph:
     def enable_cuda_graph(self, on=True):
         self._check(lib().lce_host_enable_cuda_graph(self._g, 1 if on else 0), "EnableCudaGraph")
 
+    def fuse_residual_blocks(self):
+        """LceBconv2d -> ADD [-> LceQuantize] => one node. Call before allocate_tensors."""
+        return lib().lce_host_fuse_residual_blocks(self._g)
+
     # ---- profiling / async IO (bench.py) ----
     def enable_profiling(self, on=True):
         lib().lce_host_enable_profiling(self._g, 1 if on else 0)

@@ -100,6 +100,14 @@ int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev,
                          void* out_dev, void* stream);
 int lce_b200_bconv2d_run_f32(lce_b200_bconv2d* plan, const float* in_dev,
                              void* out_dev, void* stream);
+/* Fused residual-block tail (graph-level fusion of the converter pattern
+ *   LceBconv2d(float out) -> ADD(shortcut) [-> LceQuantize of the sum]):
+ *   out = act_add(OutputTransform(acc) + residual);  packed_out = bitpack(out) (optional).
+ * Bit-identical to running the three ops one after the other. Float output plans only;
+ * packed_out additionally needs groups == 1. residual / packed_out may be NULL. */
+int lce_b200_bconv2d_run_fused(lce_b200_bconv2d* plan, const int32_t* in_dev,
+                               const float* residual_dev, int add_activation,
+                               float* out_dev, int32_t* packed_out_dev, void* stream);
 int lce_b200_bconv2d_run_host(lce_b200_bconv2d* plan, const int32_t* in_host,
                               void* out_host);
 void lce_b200_bconv2d_destroy(lce_b200_bconv2d* plan);

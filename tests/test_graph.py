@@ -183,3 +183,41 @@ def test_gpu_interpreter_predict_true_batching():
     want, _ = R.run(R.parse(blob), [x])
     assert np.abs(y - want[0]).max() < 2e-4
     it.close()
+
+
+def test_residual_block_fusion_rewrites_the_graph():
+    """Structure of the graph-level fusion (pure host logic; no device needed):
+    LceBconv2d -> ADD [-> LceQuantize] collapses into one node."""
+    g = H.HostGraph.from_tflite(zoo.quicknet(batch=1, image=64, seed=3), device_arena=True)
+    assert g.num_nodes() == 64
+    removed = g.fuse_residual_blocks()
+    # 16 ADDs + the 12 LceQuantize ops that read an ADD's output (3 per stage)
+    assert removed == 28 and g.num_nodes() == 36
+    names = [g.node_name(i) for i in range(g.num_nodes())]
+    assert names.count("LceBconv2d+ADD+LceQuantize") == 12
+    assert names.count("LceBconv2d+ADD") == 4          # last block of each stage
+    assert names.count("LceQuantize") == 4             # first block of each stage
+    assert "builtin:0" not in names and "LceBconv2d" not in names
+    assert g.fuse_residual_blocks() == 0               # idempotent
+    g.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["quicknet", "birealnet18"])
+def test_gpu_fused_graph_is_bit_identical_to_unfused(family):
+    blob = zoo.MODELS[family](batch=1, image=64, seed=11)
+    x = np.random.default_rng(4).standard_normal((5, 64, 64, 3)).astype(np.float32)
+    outs = []
+    for fuse in (False, True):
+        g = H.HostGraph.from_tflite(blob, device_arena=True)
+        if fuse:
+            assert g.fuse_residual_blocks() > 0
+        g.resize_input(g.inputs()[0], x.shape)
+        g.allocate_tensors()
+        g.enable_cuda_graph(True)
+        for _ in range(3):                               # eager, capture, replay
+            g.write(g.inputs()[0], x)
+            g.invoke()
+        outs.append(g.read(g.outputs()[0]))
+        g.close()
+    assert np.array_equal(outs[0].view(np.uint8), outs[1].view(np.uint8))
