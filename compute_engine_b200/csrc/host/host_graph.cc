@@ -389,10 +389,11 @@ TfLiteStatus Graph::AllocateTensors() {
   for (auto& n : nodes_) {
     if (!n->initialized) {
       if (n->registration->init) {
-        const char* buf = n->node.builtin_data
-                              ? static_cast<const char*>(n->node.builtin_data)
-                              : reinterpret_cast<const char*>(n->custom_options.data());
-        const size_t len = n->node.builtin_data ? n->builtin_blob.size() : n->custom_options.size();
+        // custom ops get their flexbuffer options, builtins this host's parameter blob
+        const bool custom = !n->custom_options.empty() || !n->node.builtin_data;
+        const char* buf = custom ? reinterpret_cast<const char*>(n->custom_options.data())
+                                 : static_cast<const char*>(n->node.builtin_data);
+        const size_t len = custom ? n->custom_options.size() : n->builtin_blob.size();
         n->node.user_data = n->registration->init(&ctx_, buf, len);
       }
       n->initialized = true;

@@ -55,27 +55,34 @@ struct ConvGeom {
   int B, H, W, Cin, KH, KW, Cout, sh, sw, dh, dw, ph, pw, OH, OW, act;
 };
 
-// ---- small-K direct convolution: one thread = one output pixel x 16 channels ----
-// (stem 3x3x3->16 and the 16->64 pointwise: K <= 64). Weights for the CTA's channel
-// group sit in shared memory as [K][16].
-constexpr int kDirectMaxK = 64;
+// ---- small-K direct convolution (stem 3x3x3->16, 16->64 pointwise: K <= 32) --------
+// One thread = one output pixel x 16 consecutive output channels; consecutive lanes
+// take consecutive 16-channel groups of the same pixel, so a warp writes one
+// contiguous span (coalesced 128-bit stores) and reads each input value once
+// (broadcast). All weights sit in shared memory as [K][group][16 (+4 pad)].
+constexpr int kDirectMaxK = 32;
+constexpr int kDirectMaxCout = 128;
+constexpr int kDirectGroupStride = 20;   // 16 + 4 floats: conflict-free LDS.128 across groups
 __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ filter,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ out, ConvGeom g,
-                                                            long long M) {
-  __shared__ float w_s[kDirectMaxK][16];
-  __shared__ float b_s[16];
+                                                            long long M, int G) {
+  extern __shared__ __align__(16) float w_s[];   // [K][G][20] then bias [G][16]
   const int K = g.KH * g.KW * g.Cin;
-  const int c0 = blockIdx.y * 16;
-  for (int i = threadIdx.x; i < K * 16; i += blockDim.x) {
-    const int k = i >> 4, c = i & 15;
-    w_s[k][c] = (c0 + c < g.Cout) ? filter[static_cast<size_t>(c0 + c) * K + k] : 0.0f;
+  float* b_s = w_s + K * G * kDirectGroupStride;
+  for (int i = threadIdx.x; i < K * G * 16; i += blockDim.x) {
+    const int c = i & 15, gi = (i >> 4) % G, k = (i >> 4) / G;
+    const int co = gi * 16 + c;
+    w_s[(k * G + gi) * kDirectGroupStride + c] =
+        co < g.Cout ? filter[static_cast<size_t>(co) * K + k] : 0.0f;
   }
-  if (threadIdx.x < 16)
-    b_s[threadIdx.x] = (bias && c0 + threadIdx.x < g.Cout) ? bias[c0 + threadIdx.x] : 0.0f;
+  for (int i = threadIdx.x; i < G * 16; i += blockDim.x)
+    b_s[i] = (bias && i < g.Cout) ? bias[i] : 0.0f;
   __syncthreads();
-  const long long m = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  const long long m = t / G;
+  const int gi = static_cast<int>(t - m * G);
   if (m >= M) return;
   const int ohw = g.OH * g.OW;
   const long long b = m / ohw;
@@ -84,6 +91,7 @@ __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restr
   float acc[16];
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+  const float* wp = w_s + gi * kDirectGroupStride;
   int k = 0;
   for (int fy = 0; fy < g.KH; ++fy) {
     const int iy = oy * g.sh - g.ph + fy * g.dh;
@@ -94,22 +102,31 @@ __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restr
       const float* p = in + ((b * g.H + iy) * g.W + ix) * g.Cin;
       for (int ci = 0; ci < g.Cin; ++ci, ++k) {
         const float x = inside ? __ldg(p + ci) : 0.0f;
+        const float4* w4 = reinterpret_cast<const float4*>(wp + k * G * kDirectGroupStride);
 #pragma unroll
-        for (int c = 0; c < 16; ++c) acc[c] = fmaf(x, w_s[k][c], acc[c]);
+        for (int q = 0; q < 4; ++q) {
+          const float4 w = w4[q];
+          acc[4 * q] = fmaf(x, w.x, acc[4 * q]);
+          acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
+          acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
+          acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
+        }
       }
     }
   }
+  const int c0 = gi * 16;
+  const float* bb = b_s + c0;
   float* o = out + m * g.Cout + c0;
   if (c0 + 16 <= g.Cout && (g.Cout & 3) == 0) {
 #pragma unroll
     for (int q = 0; q < 4; ++q)
       reinterpret_cast<float4*>(o)[q] =
-          make_float4(apply_act(acc[4 * q] + b_s[4 * q], g.act),
-                      apply_act(acc[4 * q + 1] + b_s[4 * q + 1], g.act),
-                      apply_act(acc[4 * q + 2] + b_s[4 * q + 2], g.act),
-                      apply_act(acc[4 * q + 3] + b_s[4 * q + 3], g.act));
+          make_float4(apply_act(acc[4 * q] + bb[4 * q], g.act),
+                      apply_act(acc[4 * q + 1] + bb[4 * q + 1], g.act),
+                      apply_act(acc[4 * q + 2] + bb[4 * q + 2], g.act),
+                      apply_act(acc[4 * q + 3] + bb[4 * q + 3], g.act));
   } else {
-    for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[c] + b_s[c], g.act);
+    for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[c] + bb[c], g.act);
   }
 }
 
@@ -430,9 +447,12 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   const long long M = static_cast<long long>(g.B) * g.OH * g.OW;
   if (M == 0) return 0;
   const int K = g.KH * g.KW * g.Cin;
-  if (K <= kDirectMaxK) {
-    dim3 grid(static_cast<unsigned>((M + 255) / 256), (g.Cout + 15) / 16);
-    conv_direct16_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, M);
+  if (K <= kDirectMaxK && g.Cout <= kDirectMaxCout && !((uintptr_t)out & 15)) {
+    const int G = (g.Cout + 15) / 16;
+    const long long threads = M * G;
+    const size_t smem = (static_cast<size_t>(K) * G * kDirectGroupStride + G * 16) * sizeof(float);
+    conv_direct16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, smem,
+                           as_stream(stream)>>>(in, filter, bias, out, g, M, G);
     return launch_check("conv_direct16_kernel");
   }
   dim3 grid(static_cast<unsigned>((M + kGM - 1) / kGM), (g.Cout + kGN - 1) / kGN);
