@@ -136,22 +136,31 @@ __device__ __forceinline__ void load_words<4>(const uint4* p, uint32_t* dst) {
   dst[0] = v.x; dst[1] = v.y; dst[2] = v.z; dst[3] = v.w;
 }
 
-// Carry-save adder on bit-planes: a + b + c = s + 2*cy, two LOP3s.
+// Carry-save adder on bit-planes: a + b + c = s + 2*cy. Written as two explicit
+// LOP3s (xor3 = 0x96, majority = 0xE8) so that exactly 2 ALU-pipe instructions are
+// emitted per adder (left to the compiler the expression is re-associated into
+// 3-4 LOP3s, and the ALU pipe -- not the POPC pipe -- becomes the limiter).
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& s,
                                     uint32_t& cy) {
-  s = a ^ b ^ c;
-  cy = (a & b) | (c & (a ^ b));
+  asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(c));
+  asm("lop3.b32 %0, %1, %2, %3, 0xE8;" : "=r"(cy) : "r"(a), "r"(b), "r"(c));
 }
 // sum_k popc(a[k] ^ w[k]) over 8 words with 4 POPCs:
 //   x0+x1+x2 = s1+2c1, x3+x4+x5 = s2+2c2, s1+s2+x6 = s3+2c3, c1+c2+c3 = s4+2c4
 //   => total = popc(s3) + popc(x7) + 2*popc(s4) + 4*popc(c4)      (exact integers)
-__device__ __forceinline__ int xor_popc8(const uint32_t* a, const uint32_t* w) {
+// 8 XOR + 8 LOP3 on the ALU pipe, 4 POPC on the XU pipe, 1 IADD3 + 2 IMAD to accumulate
+// (the multiply-adds run on the FMA pipe, which is otherwise idle here).
+__device__ __forceinline__ int xor_popc8_acc(const uint32_t* a, const uint32_t* w, int acc) {
   uint32_t s1, c1, s2, c2, s3, c3, s4, c4;
   csa(a[0] ^ w[0], a[1] ^ w[1], a[2] ^ w[2], s1, c1);
   csa(a[3] ^ w[3], a[4] ^ w[4], a[5] ^ w[5], s2, c2);
   csa(s1, s2, a[6] ^ w[6], s3, c3);
   csa(c1, c2, c3, s4, c4);
-  return __popc(s3) + __popc(a[7] ^ w[7]) + 2 * __popc(s4) + 4 * __popc(c4);
+  acc += __popc(s3) + __popc(a[7] ^ w[7]);
+  int r;
+  asm("mad.lo.s32 %0, %1, 2, %2;" : "=r"(r) : "r"(__popc(s4)), "r"(acc));
+  asm("mad.lo.s32 %0, %1, 4, %2;" : "=r"(acc) : "r"(__popc(c4)), "r"(r));
+  return acc;
 }
 
 // OutputTransform<float>::Run, output_transform.h:100-106: shift, int32 clamp,
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(kThreads, 2) bconv_kernel(const ConvKParams p)
 #pragma unroll
         for (int gq = 0; gq < G; ++gq) load_words<V>(w_ptr + (kv + gq) * kBN + j * 8, &w[gq * V]);
 #pragma unroll
-        for (int i = 0; i < kTM; ++i) acc[i][j] += xor_popc8(a[i], w);
+        for (int i = 0; i < kTM; ++i) acc[i][j] = xor_popc8_acc(a[i], w, acc[i][j]);
       }
     }
     for (; kv < nkv; ++kv) {  // K tail (< 8 words): plain XOR + POPC
