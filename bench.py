@@ -43,6 +43,16 @@ METRIC = {"quicknet": "quicknet_images_per_sec", "quicknet_large": "quicknet_lar
           "bgemm_sweep": "bgemm_binary_tops"}
 
 
+# Libraries (NCCL's version banner, ...) may write to fd 1; the contract is ONE JSON line on
+# stdout, so fd 1 is pointed at stderr for the whole run and the result goes to the saved fd.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(obj):
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
 def parse_args():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -214,12 +224,12 @@ def main_reference(args):
     if int(os.environ.get("RANK", "0")) != 0:
         return
     if args.workload == "bgemm_sweep":
-        print(json.dumps({"impl": "reference", "unavailable": "bgemm_sweep has no reference arm"}))
+        emit({"impl": "reference", "unavailable": "bgemm_sweep has no reference arm"})
         return
     steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
     n_img = min(args.batch, 64 if args.workload != "bconv_stack" else 256)
     r = run_reference(args.workload, n_img, steps, warm)
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC[args.workload], "value": r["images_per_s"],
         "unit": "images/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
         "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
@@ -230,7 +240,7 @@ def main_reference(args):
                          "kind": r["kind"], "sample": r["sample"]},
         "e2e": {"value": r["images_per_s"], "unit": "images/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
+        "gpu_launches": 0})
 
 
 # --------------------------------------------------------------------------- #
@@ -542,14 +552,14 @@ def main_b200(args):
         rows = bgemm_sweep(args, D)
         if D.rank == 0:
             best = max(rows, key=lambda r: r["binary_TOPS"])
-            print(json.dumps({"metric": METRIC["bgemm_sweep"], "value": best["binary_TOPS"],
+            emit({"metric": METRIC["bgemm_sweep"], "value": best["binary_TOPS"],
                               "unit": "binary TOPS", "n_gpus": D.world, "steps": 7, "warmup": 3,
                               "ms_per_step": best["ms"], "higher_is_better": True,
                               "scaling": "strong", "vs_baseline": None, "dtype": "u32 xor-popcount",
                               "data": "synthetic",
                               "config": {"workload": "bgemm_sweep", "best_point": best,
                                          "points": len(rows),
-                                         "l2": "192 MiB flush between launches"}}))
+                                         "l2": "192 MiB flush between launches"}})
         if D.world > 1:
             D.dist.destroy_process_group()
         return
@@ -601,7 +611,7 @@ def main_b200(args):
             line["cpu_baseline"] = {"value": ref["images_per_s"], "unit": "images/s",
                                     "cores": ref["cores"], "kind": ref["kind"],
                                     "sample": ref["sample"]}
-        print(json.dumps(line))
+        emit(line)
     if D.world > 1:
         D.dist.destroy_process_group()
 

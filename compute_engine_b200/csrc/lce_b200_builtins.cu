@@ -63,13 +63,17 @@ struct ConvGeom {
 constexpr int kDirectMaxK = 32;
 constexpr int kDirectMaxCout = 128;
 constexpr int kDirectGroupStride = 20;   // 16 + 4 floats: conflict-free LDS.128 across groups
+// KH/KW/CIN > 0: compile-time shape (stem 3x3x3, pointwise 1x1x16) so the K loop is fully
+// unrolled and every input load is in flight before the first FMA; 0 = runtime shape.
+template <int KH_, int KW_, int CIN_>
 __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ filter,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ out, ConvGeom g,
                                                             long long M, int G) {
   extern __shared__ __align__(16) float w_s[];   // [K][G][20] then bias [G][16]
-  const int K = g.KH * g.KW * g.Cin;
+  const int KH = KH_ ? KH_ : g.KH, KW = KW_ ? KW_ : g.KW, CIN = CIN_ ? CIN_ : g.Cin;
+  const int K = KH * KW * CIN;
   float* b_s = w_s + K * G * kDirectGroupStride;
   for (int i = threadIdx.x; i < K * G * 16; i += blockDim.x) {
     const int c = i & 15, gi = (i >> 4) % G, k = (i >> 4) / G;
@@ -92,25 +96,53 @@ __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restr
 #pragma unroll
   for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
   const float* wp = w_s + gi * kDirectGroupStride;
-  int k = 0;
-  for (int fy = 0; fy < g.KH; ++fy) {
-    const int iy = oy * g.sh - g.ph + fy * g.dh;
-    for (int fx = 0; fx < g.KW; ++fx) {
-      const int ix = ox * g.sw - g.pw + fx * g.dw;
-      const bool inside = static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
-                          static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
-      const float* p = in + ((b * g.H + iy) * g.W + ix) * g.Cin;
-      for (int ci = 0; ci < g.Cin; ++ci, ++k) {
-        const float x = inside ? __ldg(p + ci) : 0.0f;
-        const float4* w4 = reinterpret_cast<const float4*>(wp + k * G * kDirectGroupStride);
+  auto fma16 = [&](float x, int k) {
+    const float4* w4 = reinterpret_cast<const float4*>(wp + k * G * kDirectGroupStride);
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 w = w4[q];
-          acc[4 * q] = fmaf(x, w.x, acc[4 * q]);
-          acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
-          acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
-          acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
+    for (int q = 0; q < 4; ++q) {
+      const float4 w = w4[q];
+      acc[4 * q] = fmaf(x, w.x, acc[4 * q]);
+      acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
+      acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
+      acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
+    }
+  };
+  if (KH_ > 0) {
+    float xin[(KH_ > 0 ? KH_ * KW_ * CIN_ : 1)];
+#pragma unroll
+    for (int fy = 0; fy < KH_; ++fy)
+#pragma unroll
+      for (int fx = 0; fx < KW_; ++fx) {
+        const int iy = oy * g.sh - g.ph + fy * g.dh, ix = ox * g.sw - g.pw + fx * g.dw;
+        const bool inside = static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
+                            static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
+        const float* p = in + ((b * g.H + iy) * g.W + ix) * CIN_;
+        if (CIN_ % 4 == 0) {
+#pragma unroll
+          for (int c4 = 0; c4 < CIN_ / 4; ++c4) {
+            const float4 v = inside ? __ldg(reinterpret_cast<const float4*>(p) + c4)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
+            float* d = &xin[(fy * KW_ + fx) * CIN_ + c4 * 4];
+            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+          }
+        } else {
+#pragma unroll
+          for (int ci = 0; ci < CIN_; ++ci)
+            xin[(fy * KW_ + fx) * CIN_ + ci] = inside ? __ldg(p + ci) : 0.0f;
         }
+      }
+#pragma unroll
+    for (int k = 0; k < KH_ * KW_ * CIN_; ++k) fma16(xin[k], k);
+  } else {
+    int k = 0;
+    for (int fy = 0; fy < KH; ++fy) {
+      const int iy = oy * g.sh - g.ph + fy * g.dh;
+      for (int fx = 0; fx < KW; ++fx) {
+        const int ix = ox * g.sw - g.pw + fx * g.dw;
+        const bool inside = static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
+                            static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
+        const float* p = in + ((b * g.H + iy) * g.W + ix) * CIN;
+        for (int ci = 0; ci < CIN; ++ci, ++k) fma16(inside ? __ldg(p + ci) : 0.0f, k);
       }
     }
   }
@@ -127,6 +159,94 @@ __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restr
                       apply_act(acc[4 * q + 3] + bb[4 * q + 3], g.act));
   } else {
     for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[c] + bb[c], g.act);
+  }
+}
+
+// ---- plain-GEMM convolution (1x1, stride 1: A = [M, K] row-major): 128x128x16 tiles, 8x8
+// outputs per thread, 128-bit global loads along K, register-prefetch double buffering ----
+constexpr int kPM = 128, kPN = 128, kPK = 16;
+__global__ void __launch_bounds__(256) conv_gemm128_kernel(const float* __restrict__ A,
+                                                           const float* __restrict__ Wt,
+                                                           const float* __restrict__ bias,
+                                                           float* __restrict__ out, long long M,
+                                                           int N, int K, int act) {
+  __shared__ __align__(16) float A_s[2][kPK][kPM + 4];
+  __shared__ __align__(16) float B_s[2][kPK][kPN + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kPM;
+  const int n0 = blockIdx.y * kPN;
+  // loader mapping: 2 float4 of A and 2 of B per thread per K-chunk
+  const int lrow = tid >> 2;          // 0..63 (+64)
+  const int lk = (tid & 3) * 4;       // 0,4,8,12
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  float4 ra[2], rb[2];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const long long m = m0 + lrow + 64 * h;
+      const int n = n0 + lrow + 64 * h;
+      const int k = k0 + lk;
+      ra[h] = (m < M && k < K) ? __ldg(reinterpret_cast<const float4*>(A + m * K + k))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+      rb[h] = (n < N && k < K) ? __ldg(reinterpret_cast<const float4*>(Wt + static_cast<size_t>(n) * K + k))
+                               : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int r = lrow + 64 * h;
+      A_s[buf][lk][r] = ra[h].x; A_s[buf][lk + 1][r] = ra[h].y;
+      A_s[buf][lk + 2][r] = ra[h].z; A_s[buf][lk + 3][r] = ra[h].w;
+      B_s[buf][lk][r] = rb[h].x; B_s[buf][lk + 1][r] = rb[h].y;
+      B_s[buf][lk + 2][r] = rb[h].z; B_s[buf][lk + 3][r] = rb[h].w;
+    }
+  };
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  const int nk = (K + kPK - 1) / kPK;
+  for (int it = 0; it < nk; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < nk) fetch((it + 1) * kPK);
+#pragma unroll
+    for (int kk = 0; kk < kPK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&A_s[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&A_s[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&B_s[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&B_s[buf][kk][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (it + 1 < nk) {
+      stash(buf ^ 1);
+      __syncthreads();
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 64 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        v[q] = apply_act(acc[i][jh * 4 + q] + ((bias && n + q < N) ? bias[n + q] : 0.0f), act);
+      float* o = out + m * N + n;
+      if (n + 3 < N && (N & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      else
+        for (int q = 0; q < 4 && n + q < N; ++q) o[q] = v[q];
+    }
   }
 }
 
@@ -451,9 +571,25 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
     const int G = (g.Cout + 15) / 16;
     const long long threads = M * G;
     const size_t smem = (static_cast<size_t>(K) * G * kDirectGroupStride + G * 16) * sizeof(float);
-    conv_direct16_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, smem,
-                           as_stream(stream)>>>(in, filter, bias, out, g, M, G);
+    const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+    if (g.KH == 3 && g.KW == 3 && g.Cin == 3)
+      conv_direct16_kernel<3, 3, 3><<<blocks, 256, smem, as_stream(stream)>>>(in, filter, bias, out,
+                                                                              g, M, G);
+    else if (g.KH == 1 && g.KW == 1 && g.Cin == 16 && !((uintptr_t)in & 15))
+      conv_direct16_kernel<1, 1, 16><<<blocks, 256, smem, as_stream(stream)>>>(in, filter, bias,
+                                                                               out, g, M, G);
+    else
+      conv_direct16_kernel<0, 0, 0><<<blocks, 256, smem, as_stream(stream)>>>(in, filter, bias, out,
+                                                                              g, M, G);
     return launch_check("conv_direct16_kernel");
+  }
+  const bool plain = g.KH == 1 && g.KW == 1 && g.sh == 1 && g.sw == 1 && (K & 3) == 0 &&
+                     !((uintptr_t)in & 15) && !((uintptr_t)filter & 15) && !((uintptr_t)out & 15);
+  if (plain) {
+    dim3 grid(static_cast<unsigned>((M + kPM - 1) / kPM), (g.Cout + kPN - 1) / kPN);
+    conv_gemm128_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, M, g.Cout, K,
+                                                             g.act);
+    return launch_check("conv_gemm128_kernel");
   }
   dim3 grid(static_cast<unsigned>((M + kGM - 1) / kGM), (g.Cout + kGN - 1) / kGN);
   conv_gemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, M);
