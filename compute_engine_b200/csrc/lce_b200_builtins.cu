@@ -84,13 +84,17 @@ __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restr
   for (int i = threadIdx.x; i < G * 16; i += blockDim.x)
     b_s[i] = (bias && i < g.Cout) ? bias[i] : 0.0f;
   __syncthreads();
-  const long long t = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
-  const long long m = t / G;
-  const int gi = static_cast<int>(t - m * G);
-  if (m >= M) return;
-  const int ohw = g.OH * g.OW;
-  const long long b = m / ohw;
-  const int r = static_cast<int>(m - b * ohw);
+  // 32-bit index arithmetic (the host guarantees M * G < 2^31): 64-bit divisions would cost
+  // more instructions than the convolution itself
+  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
+  const unsigned mu = t / static_cast<unsigned>(G);
+  const int gi = static_cast<int>(t - mu * G);
+  if (mu >= static_cast<unsigned>(M)) return;
+  const long long m = mu;
+  const unsigned ohw = g.OH * g.OW;
+  const unsigned bu = mu / ohw;
+  const long long b = bu;
+  const int r = static_cast<int>(mu - bu * ohw);
   const int oy = r / g.OW, ox = r - oy * g.OW;
   float acc[16];
 #pragma unroll
@@ -369,21 +373,22 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
 }
 
 // 4 channels per thread (C % 4 == 0): 128-bit loads of inputs, weights and outputs.
+template <typename I>   // I = unsigned when the element count fits 32 bits (cheap div/mod)
 __global__ void __launch_bounds__(256) depthwise_v4_kernel(const float4* __restrict__ in,
                                                            const float4* __restrict__ filter,
                                                            const float4* __restrict__ bias,
                                                            float4* __restrict__ out, ConvGeom g,
-                                                           long long n4) {
-  const int C4 = g.Cout >> 2;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n4;
-       i += stride) {
+                                                           long long n4_) {
+  const I C4 = g.Cout >> 2;
+  const I n4 = static_cast<I>(n4_);
+  const I stride = static_cast<I>(gridDim.x) * blockDim.x;
+  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
     const int c = static_cast<int>(i % C4);
-    long long r = i / C4;
-    const int ox = static_cast<int>(r % g.OW);
-    r /= g.OW;
-    const int oy = static_cast<int>(r % g.OH);
-    const long long b = r / g.OH;
+    I r = i / C4;
+    const int ox = static_cast<int>(r % static_cast<I>(g.OW));
+    r /= static_cast<I>(g.OW);
+    const int oy = static_cast<int>(r % static_cast<I>(g.OH));
+    const long long b = r / static_cast<I>(g.OH);
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int fy = 0; fy < g.KH; ++fy) {
       const int iy = oy * g.sh - g.ph + fy * g.dh;
@@ -404,21 +409,20 @@ __global__ void __launch_bounds__(256) depthwise_v4_kernel(const float4* __restr
   }
 }
 
-template <bool MAX>
+template <bool MAX, typename I>
 __global__ void __launch_bounds__(256) pool_v4_kernel(const float4* __restrict__ in,
                                                       float4* __restrict__ out, int B, int H,
                                                       int W, int C4, int OH, int OW, int fh, int fw,
                                                       int sh, int sw, int ph, int pw, int act) {
-  const long long n = static_cast<long long>(B) * OH * OW * C4;
-  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += stride) {
-    const int c = static_cast<int>(i % C4);
-    long long r = i / C4;
-    const int ox = static_cast<int>(r % OW);
-    r /= OW;
-    const int oy = static_cast<int>(r % OH);
-    const long long b = r / OH;
+  const I n = static_cast<I>(static_cast<long long>(B) * OH * OW * C4);
+  const I stride = static_cast<I>(gridDim.x) * blockDim.x;
+  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < n; i += stride) {
+    const int c = static_cast<int>(i % static_cast<I>(C4));
+    I r = i / static_cast<I>(C4);
+    const int ox = static_cast<int>(r % static_cast<I>(OW));
+    r /= static_cast<I>(OW);
+    const int oy = static_cast<int>(r % static_cast<I>(OH));
+    const long long b = r / static_cast<I>(OH);
     const int y0 = oy * sh - ph, x0 = ox * sw - pw;
     const int ys = max(0, y0), ye = min(H, y0 + fh), xs = max(0, x0), xe = min(W, x0 + fw);
     float4 v = MAX ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX)
@@ -567,7 +571,8 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   const long long M = static_cast<long long>(g.B) * g.OH * g.OW;
   if (M == 0) return 0;
   const int K = g.KH * g.KW * g.Cin;
-  if (K <= kDirectMaxK && g.Cout <= kDirectMaxCout && !((uintptr_t)out & 15)) {
+  if (K <= kDirectMaxK && g.Cout <= kDirectMaxCout && !((uintptr_t)out & 15) &&
+      M * ((g.Cout + 15) / 16) < (1LL << 31)) {
     const int G = (g.Cout + 15) / 16;
     const long long threads = M * G;
     const size_t smem = (static_cast<size_t>(K) * G * kDirectGroupStride + G * 16) * sizeof(float);
@@ -607,9 +612,14 @@ int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in,
   const bool a16 = !((uintptr_t)in & 15) && !((uintptr_t)filter & 15) && !((uintptr_t)out & 15) &&
                    !((uintptr_t)bias & 15);
   if ((g.Cout & 3) == 0 && a16) {
-    depthwise_v4_kernel<<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
-        reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
-        reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g, n / 4);
+    if (n / 4 < (1LL << 31))
+      depthwise_v4_kernel<unsigned><<<grid_for(n / 4, 256, 1 << 22), 256, 0, as_stream(stream)>>>(
+          reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
+          reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g, n / 4);
+    else
+      depthwise_v4_kernel<long long><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+          reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
+          reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g, n / 4);
     return launch_check("depthwise_v4_kernel");
   }
   depthwise_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, n);
@@ -634,16 +644,19 @@ static int run_pool(bool is_max, const lce_f32_pool_desc* d, const float* in, fl
   const int pw = pad_before(d->stride_w, 1, d->in_w, d->filter_w, ow);
   if ((d->channels & 3) == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15)) {
     const int C4 = d->channels >> 2;
-    if (is_max)
-      pool_v4_kernel<true><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
-          reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->batch, d->in_h,
-          d->in_w, C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw,
-          d->activation);
-    else
-      pool_v4_kernel<false><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
-          reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->batch, d->in_h,
-          d->in_w, C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw,
-          d->activation);
+#define LCE_POOL_V4(MAXV, IT, GRID)                                                          \
+  pool_v4_kernel<MAXV, IT><<<GRID, 256, 0, as_stream(stream)>>>(                              \
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->batch, d->in_h, \
+      d->in_w, C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw,        \
+      d->activation)
+    if (n / 4 < (1LL << 31)) {
+      if (is_max) LCE_POOL_V4(true, unsigned, grid_for(n / 4, 256, 1 << 22));
+      else LCE_POOL_V4(false, unsigned, grid_for(n / 4, 256, 1 << 22));
+    } else {
+      if (is_max) LCE_POOL_V4(true, long long, grid_for(n / 4, 256));
+      else LCE_POOL_V4(false, long long, grid_for(n / 4, 256));
+    }
+#undef LCE_POOL_V4
     return launch_check("pool_v4_kernel");
   }
   if (is_max)

@@ -218,7 +218,10 @@ __global__ void __launch_bounds__(kThreads, 2) bconv_kernel(const ConvKParams p)
   const int32_t* img = p.in;
   if (pix_valid) {
     const int ohw = p.OH * p.OW;
-    const long long b = gm / ohw;
+    // 32-bit division when the pixel count allows it (a 64-bit divide is ~100 instructions)
+    const long long b = p.M < (1LL << 31) ? static_cast<long long>(static_cast<unsigned>(gm) /
+                                                                   static_cast<unsigned>(ohw))
+                                          : gm / ohw;
     const int r = static_cast<int>(gm - b * ohw);
     const int oy = r / p.OW;
     const int ox = r - oy * p.OW;

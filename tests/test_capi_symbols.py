@@ -76,3 +76,10 @@ def test_no_cpu_fallback_without_device(lib):
     with pytest.raises(capi.LceError, match="no CUDA device"):
         capi.BConv2d(d, np.zeros((8, 1, 1, 1), np.int32), np.ones(8, np.float32),
                      np.ones(8, np.float32))
+
+
+def test_builtin_kernels_header_symbols_are_exported(lib):
+    names = declared_symbols("lce_b200_builtins.h")
+    assert len(names) == 11
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/lce_b200_builtins.h but not exported"
