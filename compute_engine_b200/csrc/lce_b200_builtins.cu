@@ -63,10 +63,13 @@ struct ConvGeom {
 constexpr int kDirectMaxK = 32;
 constexpr int kDirectMaxCout = 128;
 constexpr int kDirectGroupStride = 20;   // 16 + 4 floats: conflict-free LDS.128 across groups
-// KH/KW/CIN > 0: compile-time shape (stem 3x3x3, pointwise 1x1x16) so the K loop is fully
-// unrolled and every input load is in flight before the first FMA; 0 = runtime shape.
+// KH/KW/CIN > 0: compile-time shape (stem 3x3x3, pointwise 1x1x16) => fully unrolled K loop.
+// Each thread computes kPX pixels x 16 channels so every 128-bit weight read from shared
+// memory feeds 4*kPX FMAs (with one pixel per thread the kernel was LDS-bound: ncu showed
+// short-scoreboard / MIO-throttle stalls dominating).
+constexpr int kPX = 4;
 template <int KH_, int KW_, int CIN_>
-__global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restrict__ in,
+__global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ filter,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ out, ConvGeom g,
@@ -84,85 +87,118 @@ __global__ void __launch_bounds__(256) conv_direct16_kernel(const float* __restr
   for (int i = threadIdx.x; i < G * 16; i += blockDim.x)
     b_s[i] = (bias && i < g.Cout) ? bias[i] : 0.0f;
   __syncthreads();
-  // 32-bit index arithmetic (the host guarantees M * G < 2^31): 64-bit divisions would cost
-  // more instructions than the convolution itself
-  const unsigned t = blockIdx.x * blockDim.x + threadIdx.x;
-  const unsigned mu = t / static_cast<unsigned>(G);
-  const int gi = static_cast<int>(t - mu * G);
-  if (mu >= static_cast<unsigned>(M)) return;
-  const long long m = mu;
+  // thread -> (pixel quad, channel group); consecutive lanes = consecutive groups, then pixels.
+  // Pixel p of a thread is m0 + p * pstride with pstride = blockDim.x / G pixels, so that for
+  // every p a warp still writes one contiguous span. 32-bit index math (host checks the range).
+  const unsigned px_per_blk = blockDim.x / static_cast<unsigned>(G);
+  const unsigned lpx = threadIdx.x / static_cast<unsigned>(G);
+  const int gi = static_cast<int>(threadIdx.x - lpx * G);
+  if (lpx >= px_per_blk) return;
+  const unsigned blk_m0 = blockIdx.x * px_per_blk * kPX;
   const unsigned ohw = g.OH * g.OW;
-  const unsigned bu = mu / ohw;
-  const long long b = bu;
-  const int r = static_cast<int>(mu - bu * ohw);
-  const int oy = r / g.OW, ox = r - oy * g.OW;
-  float acc[16];
+  long long ibase[kPX];
+  int iy0[kPX], ix0[kPX];
+  bool ok[kPX];
 #pragma unroll
-  for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+  for (int p = 0; p < kPX; ++p) {
+    const unsigned mu = blk_m0 + p * px_per_blk + lpx;
+    ok[p] = mu < static_cast<unsigned>(M);
+    const unsigned mm = ok[p] ? mu : 0u;
+    const unsigned bu = mm / ohw;
+    const unsigned r = mm - bu * ohw;
+    const unsigned oy = r / static_cast<unsigned>(g.OW), ox = r - oy * g.OW;
+    iy0[p] = static_cast<int>(oy) * g.sh - g.ph;
+    ix0[p] = static_cast<int>(ox) * g.sw - g.pw;
+    ibase[p] = static_cast<long long>(bu) * g.H * g.W;
+  }
+  float acc[kPX][16];
+#pragma unroll
+  for (int p = 0; p < kPX; ++p)
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[p][c] = 0.0f;
   const float* wp = w_s + gi * kDirectGroupStride;
-  auto fma16 = [&](float x, int k) {
+  auto fma16 = [&](const float (&x)[kPX], int k) {
     const float4* w4 = reinterpret_cast<const float4*>(wp + k * G * kDirectGroupStride);
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const float4 w = w4[q];
-      acc[4 * q] = fmaf(x, w.x, acc[4 * q]);
-      acc[4 * q + 1] = fmaf(x, w.y, acc[4 * q + 1]);
-      acc[4 * q + 2] = fmaf(x, w.z, acc[4 * q + 2]);
-      acc[4 * q + 3] = fmaf(x, w.w, acc[4 * q + 3]);
+#pragma unroll
+      for (int p = 0; p < kPX; ++p) {
+        acc[p][4 * q] = fmaf(x[p], w.x, acc[p][4 * q]);
+        acc[p][4 * q + 1] = fmaf(x[p], w.y, acc[p][4 * q + 1]);
+        acc[p][4 * q + 2] = fmaf(x[p], w.z, acc[p][4 * q + 2]);
+        acc[p][4 * q + 3] = fmaf(x[p], w.w, acc[p][4 * q + 3]);
+      }
+    }
+  };
+  auto tap = [&](int fy, int fx, int k0, int cin) {
+    const float* src[kPX];
+    bool inside[kPX];
+#pragma unroll
+    for (int p = 0; p < kPX; ++p) {
+      const int iy = iy0[p] + fy * g.dh, ix = ix0[p] + fx * g.dw;
+      inside[p] = ok[p] && static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
+                  static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
+      src[p] = in + (ibase[p] + static_cast<long long>(iy) * g.W + ix) * cin;
+    }
+    if (CIN_ > 0 && CIN_ % 4 == 0) {
+#pragma unroll
+      for (int c4 = 0; c4 < (CIN_ > 0 ? CIN_ / 4 : 1); ++c4) {
+        float4 v[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p)
+          v[p] = inside[p] ? __ldg(reinterpret_cast<const float4*>(src[p]) + c4)
+                           : make_float4(0.f, 0.f, 0.f, 0.f);
+        float x[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) x[p] = v[p].x;
+        fma16(x, k0 + c4 * 4);
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) x[p] = v[p].y;
+        fma16(x, k0 + c4 * 4 + 1);
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) x[p] = v[p].z;
+        fma16(x, k0 + c4 * 4 + 2);
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) x[p] = v[p].w;
+        fma16(x, k0 + c4 * 4 + 3);
+      }
+    } else {
+      for (int ci = 0; ci < cin; ++ci) {
+        float x[kPX];
+#pragma unroll
+        for (int p = 0; p < kPX; ++p) x[p] = inside[p] ? __ldg(src[p] + ci) : 0.0f;
+        fma16(x, k0 + ci);
+      }
     }
   };
   if (KH_ > 0) {
-    float xin[(KH_ > 0 ? KH_ * KW_ * CIN_ : 1)];
 #pragma unroll
-    for (int fy = 0; fy < KH_; ++fy)
+    for (int fy = 0; fy < (KH_ > 0 ? KH_ : 1); ++fy)
 #pragma unroll
-      for (int fx = 0; fx < KW_; ++fx) {
-        const int iy = oy * g.sh - g.ph + fy * g.dh, ix = ox * g.sw - g.pw + fx * g.dw;
-        const bool inside = static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
-                            static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
-        const float* p = in + ((b * g.H + iy) * g.W + ix) * CIN_;
-        if (CIN_ % 4 == 0) {
-#pragma unroll
-          for (int c4 = 0; c4 < CIN_ / 4; ++c4) {
-            const float4 v = inside ? __ldg(reinterpret_cast<const float4*>(p) + c4)
-                                    : make_float4(0.f, 0.f, 0.f, 0.f);
-            float* d = &xin[(fy * KW_ + fx) * CIN_ + c4 * 4];
-            d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
-          }
-        } else {
-#pragma unroll
-          for (int ci = 0; ci < CIN_; ++ci)
-            xin[(fy * KW_ + fx) * CIN_ + ci] = inside ? __ldg(p + ci) : 0.0f;
-        }
-      }
-#pragma unroll
-    for (int k = 0; k < KH_ * KW_ * CIN_; ++k) fma16(xin[k], k);
+      for (int fx = 0; fx < (KW_ > 0 ? KW_ : 1); ++fx) tap(fy, fx, (fy * KW_ + fx) * CIN_, CIN_);
   } else {
-    int k = 0;
-    for (int fy = 0; fy < KH; ++fy) {
-      const int iy = oy * g.sh - g.ph + fy * g.dh;
-      for (int fx = 0; fx < KW; ++fx) {
-        const int ix = ox * g.sw - g.pw + fx * g.dw;
-        const bool inside = static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
-                            static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
-        const float* p = in + ((b * g.H + iy) * g.W + ix) * CIN;
-        for (int ci = 0; ci < CIN; ++ci, ++k) fma16(inside ? __ldg(p + ci) : 0.0f, k);
-      }
-    }
+    for (int fy = 0; fy < KH; ++fy)
+      for (int fx = 0; fx < KW; ++fx) tap(fy, fx, (fy * KW + fx) * CIN, CIN);
   }
   const int c0 = gi * 16;
   const float* bb = b_s + c0;
-  float* o = out + m * g.Cout + c0;
-  if (c0 + 16 <= g.Cout && (g.Cout & 3) == 0) {
 #pragma unroll
-    for (int q = 0; q < 4; ++q)
-      reinterpret_cast<float4*>(o)[q] =
-          make_float4(apply_act(acc[4 * q] + bb[4 * q], g.act),
-                      apply_act(acc[4 * q + 1] + bb[4 * q + 1], g.act),
-                      apply_act(acc[4 * q + 2] + bb[4 * q + 2], g.act),
-                      apply_act(acc[4 * q + 3] + bb[4 * q + 3], g.act));
-  } else {
-    for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[c] + bb[c], g.act);
+  for (int p = 0; p < kPX; ++p) {
+    if (!ok[p]) continue;
+    const long long m = static_cast<long long>(blk_m0) + p * px_per_blk + lpx;
+    float* o = out + m * g.Cout + c0;
+    if (c0 + 16 <= g.Cout && (g.Cout & 3) == 0) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        reinterpret_cast<float4*>(o)[q] =
+            make_float4(apply_act(acc[p][4 * q] + bb[4 * q], g.act),
+                        apply_act(acc[p][4 * q + 1] + bb[4 * q + 1], g.act),
+                        apply_act(acc[p][4 * q + 2] + bb[4 * q + 2], g.act),
+                        apply_act(acc[p][4 * q + 3] + bb[4 * q + 3], g.act));
+    } else {
+      for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[p][c] + bb[c], g.act);
+    }
   }
 }
 
@@ -372,74 +408,81 @@ __global__ void __launch_bounds__(256) depthwise_kernel(const float* __restrict_
   }
 }
 
-// 4 channels per thread (C % 4 == 0): 128-bit loads of inputs, weights and outputs.
-template <typename I>   // I = unsigned when the element count fits 32 bits (cheap div/mod)
+// 4 channels per thread (C % 4 == 0): 128-bit loads of inputs, weights and outputs. 3-D grid
+// (x: (ox, c4), y: oy, z: batch) -- the flat-index version spent most of its instructions on
+// integer div/mod (ncu: issue-bound at ~30 % of DRAM bandwidth).
+template <int KHW>   // KHW = 3: 3x3 window fully unrolled (all loads in flight); 0: runtime
 __global__ void __launch_bounds__(256) depthwise_v4_kernel(const float4* __restrict__ in,
                                                            const float4* __restrict__ filter,
                                                            const float4* __restrict__ bias,
-                                                           float4* __restrict__ out, ConvGeom g,
-                                                           long long n4_) {
-  const I C4 = g.Cout >> 2;
-  const I n4 = static_cast<I>(n4_);
-  const I stride = static_cast<I>(gridDim.x) * blockDim.x;
-  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < n4; i += stride) {
-    const int c = static_cast<int>(i % C4);
-    I r = i / C4;
-    const int ox = static_cast<int>(r % static_cast<I>(g.OW));
-    r /= static_cast<I>(g.OW);
-    const int oy = static_cast<int>(r % static_cast<I>(g.OH));
-    const long long b = r / static_cast<I>(g.OH);
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int fy = 0; fy < g.KH; ++fy) {
-      const int iy = oy * g.sh - g.ph + fy * g.dh;
-      if (static_cast<unsigned>(iy) >= static_cast<unsigned>(g.H)) continue;
-      for (int fx = 0; fx < g.KW; ++fx) {
-        const int ix = ox * g.sw - g.pw + fx * g.dw;
-        if (static_cast<unsigned>(ix) >= static_cast<unsigned>(g.W)) continue;
-        const float4 x = __ldg(in + ((b * g.H + iy) * g.W + ix) * C4 + c);
-        const float4 w = __ldg(filter + (fy * g.KW + fx) * C4 + c);
-        acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y);
-        acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
-      }
+                                                           float4* __restrict__ out, ConvGeom g) {
+  const int C4 = g.Cout >> 2;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= g.OW * C4) return;
+  const int ox = i / C4, c = i - ox * C4;
+  const int oy = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int KH = KHW ? KHW : g.KH, KW = KHW ? KHW : g.KW;
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* img = in + b * g.H * g.W * C4 + c;
+#pragma unroll
+  for (int fy = 0; fy < KH; ++fy) {
+    const int iy = oy * g.sh - g.ph + fy * g.dh;
+    if (static_cast<unsigned>(iy) >= static_cast<unsigned>(g.H)) continue;
+#pragma unroll
+    for (int fx = 0; fx < KW; ++fx) {
+      const int ix = ox * g.sw - g.pw + fx * g.dw;
+      if (static_cast<unsigned>(ix) >= static_cast<unsigned>(g.W)) continue;
+      const float4 x = __ldg(img + (static_cast<long long>(iy) * g.W + ix) * C4);
+      const float4 w = __ldg(filter + (fy * KW + fx) * C4 + c);
+      acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y);
+      acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
     }
-    float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (bias) bb = __ldg(bias + c);
-    out[i] = make_float4(apply_act(acc.x + bb.x, g.act), apply_act(acc.y + bb.y, g.act),
-                         apply_act(acc.z + bb.z, g.act), apply_act(acc.w + bb.w, g.act));
   }
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bb = __ldg(bias + c);
+  out[((b * g.OH + oy) * g.OW + ox) * C4 + c] =
+      make_float4(apply_act(acc.x + bb.x, g.act), apply_act(acc.y + bb.y, g.act),
+                  apply_act(acc.z + bb.z, g.act), apply_act(acc.w + bb.w, g.act));
 }
 
-template <bool MAX, typename I>
+template <bool MAX, int FHW>   // FHW = 2 / 3: window fully unrolled; 0: runtime
 __global__ void __launch_bounds__(256) pool_v4_kernel(const float4* __restrict__ in,
-                                                      float4* __restrict__ out, int B, int H,
-                                                      int W, int C4, int OH, int OW, int fh, int fw,
+                                                      float4* __restrict__ out, int H, int W,
+                                                      int C4, int OH, int OW, int fh_, int fw_,
                                                       int sh, int sw, int ph, int pw, int act) {
-  const I n = static_cast<I>(static_cast<long long>(B) * OH * OW * C4);
-  const I stride = static_cast<I>(gridDim.x) * blockDim.x;
-  for (I i = blockIdx.x * static_cast<I>(blockDim.x) + threadIdx.x; i < n; i += stride) {
-    const int c = static_cast<int>(i % static_cast<I>(C4));
-    I r = i / static_cast<I>(C4);
-    const int ox = static_cast<int>(r % static_cast<I>(OW));
-    r /= static_cast<I>(OW);
-    const int oy = static_cast<int>(r % static_cast<I>(OH));
-    const long long b = r / static_cast<I>(OH);
-    const int y0 = oy * sh - ph, x0 = ox * sw - pw;
-    const int ys = max(0, y0), ye = min(H, y0 + fh), xs = max(0, x0), xe = min(W, x0 + fw);
-    float4 v = MAX ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX)
-                   : make_float4(0.f, 0.f, 0.f, 0.f);
-    for (int y = ys; y < ye; ++y)
-      for (int x = xs; x < xe; ++x) {
-        const float4 e = __ldg(in + ((b * H + y) * W + x) * C4 + c);
-        if (MAX) { v.x = fmaxf(v.x, e.x); v.y = fmaxf(v.y, e.y); v.z = fmaxf(v.z, e.z); v.w = fmaxf(v.w, e.w); }
-        else { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
-      }
-    if (!MAX) {
-      const float d = static_cast<float>(max(1, (ye - ys) * (xe - xs)));
-      v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OW * C4) return;
+  const int ox = i / C4, c = i - ox * C4;
+  const int oy = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int fh = FHW ? FHW : fh_, fw = FHW ? FHW : fw_;
+  const int y0 = oy * sh - ph, x0 = ox * sw - pw;
+  const float4* img = in + b * H * W * C4 + c;
+  float4 v = MAX ? make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX)
+                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  int cnt = 0;
+#pragma unroll
+  for (int fy = 0; fy < fh; ++fy) {
+    const int y = y0 + fy;
+    if (static_cast<unsigned>(y) >= static_cast<unsigned>(H)) continue;
+#pragma unroll
+    for (int fx = 0; fx < fw; ++fx) {
+      const int x = x0 + fx;
+      if (static_cast<unsigned>(x) >= static_cast<unsigned>(W)) continue;
+      const float4 e = __ldg(img + (static_cast<long long>(y) * W + x) * C4);
+      ++cnt;
+      if (MAX) { v.x = fmaxf(v.x, e.x); v.y = fmaxf(v.y, e.y); v.z = fmaxf(v.z, e.z); v.w = fmaxf(v.w, e.w); }
+      else { v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
     }
-    out[i] = make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act),
-                         apply_act(v.w, act));
   }
+  if (!MAX) {
+    const float d = static_cast<float>(max(1, cnt));
+    v.x = v.x / d; v.y = v.y / d; v.z = v.z / d; v.w = v.w / d;
+  }
+  out[((b * OH + oy) * OW + ox) * C4 + c] =
+      make_float4(apply_act(v.x, act), apply_act(v.y, act), apply_act(v.z, act),
+                  apply_act(v.w, act));
 }
 
 template <bool MAX>
@@ -572,19 +615,22 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   if (M == 0) return 0;
   const int K = g.KH * g.KW * g.Cin;
   if (K <= kDirectMaxK && g.Cout <= kDirectMaxCout && !((uintptr_t)out & 15) &&
-      M * ((g.Cout + 15) / 16) < (1LL << 31)) {
+      M * ((g.Cout + 15) / 16) < (1LL << 30)) {
     const int G = (g.Cout + 15) / 16;
     const long long threads = M * G;
     const size_t smem = (static_cast<size_t>(K) * G * kDirectGroupStride + G * 16) * sizeof(float);
-    const unsigned blocks = static_cast<unsigned>((threads + 255) / 256);
+    // 128 threads = (128 / G) pixels x G groups, kPX pixels each
+    const int px_per_blk = 128 / G;
+    const unsigned blocks = static_cast<unsigned>((M + px_per_blk * kPX - 1) / (px_per_blk * kPX));
+    (void)threads;
     if (g.KH == 3 && g.KW == 3 && g.Cin == 3)
-      conv_direct16_kernel<3, 3, 3><<<blocks, 256, smem, as_stream(stream)>>>(in, filter, bias, out,
+      conv_direct16_kernel<3, 3, 3><<<blocks, 128, smem, as_stream(stream)>>>(in, filter, bias, out,
                                                                               g, M, G);
     else if (g.KH == 1 && g.KW == 1 && g.Cin == 16 && !((uintptr_t)in & 15))
-      conv_direct16_kernel<1, 1, 16><<<blocks, 256, smem, as_stream(stream)>>>(in, filter, bias,
+      conv_direct16_kernel<1, 1, 16><<<blocks, 128, smem, as_stream(stream)>>>(in, filter, bias,
                                                                                out, g, M, G);
     else
-      conv_direct16_kernel<0, 0, 0><<<blocks, 256, smem, as_stream(stream)>>>(in, filter, bias, out,
+      conv_direct16_kernel<0, 0, 0><<<blocks, 128, smem, as_stream(stream)>>>(in, filter, bias, out,
                                                                               g, M, G);
     return launch_check("conv_direct16_kernel");
   }
@@ -611,15 +657,17 @@ int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in,
   if (n == 0) return 0;
   const bool a16 = !((uintptr_t)in & 15) && !((uintptr_t)filter & 15) && !((uintptr_t)out & 15) &&
                    !((uintptr_t)bias & 15);
-  if ((g.Cout & 3) == 0 && a16) {
-    if (n / 4 < (1LL << 31))
-      depthwise_v4_kernel<unsigned><<<grid_for(n / 4, 256, 1 << 22), 256, 0, as_stream(stream)>>>(
+  if ((g.Cout & 3) == 0 && a16 && g.B <= 65535 && g.OH <= 65535) {
+    const int C4 = g.Cout >> 2;
+    dim3 grid((g.OW * C4 + 255) / 256, g.OH, g.B);
+    if (g.KH == 3 && g.KW == 3)
+      depthwise_v4_kernel<3><<<grid, 256, 0, as_stream(stream)>>>(
           reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
-          reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g, n / 4);
+          reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g);
     else
-      depthwise_v4_kernel<long long><<<grid_for(n / 4, 256), 256, 0, as_stream(stream)>>>(
+      depthwise_v4_kernel<0><<<grid, 256, 0, as_stream(stream)>>>(
           reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
-          reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g, n / 4);
+          reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), g);
     return launch_check("depthwise_v4_kernel");
   }
   depthwise_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, n);
@@ -642,19 +690,20 @@ static int run_pool(bool is_max, const lce_f32_pool_desc* d, const float* in, fl
   if (n <= 0) return 0;
   const int ph = pad_before(d->stride_h, 1, d->in_h, d->filter_h, oh);
   const int pw = pad_before(d->stride_w, 1, d->in_w, d->filter_w, ow);
-  if ((d->channels & 3) == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15)) {
+  if ((d->channels & 3) == 0 && !((uintptr_t)in & 15) && !((uintptr_t)out & 15) &&
+      d->batch <= 65535 && oh <= 65535) {
     const int C4 = d->channels >> 2;
-#define LCE_POOL_V4(MAXV, IT, GRID)                                                          \
-  pool_v4_kernel<MAXV, IT><<<GRID, 256, 0, as_stream(stream)>>>(                              \
-      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->batch, d->in_h, \
-      d->in_w, C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw,        \
-      d->activation)
-    if (n / 4 < (1LL << 31)) {
-      if (is_max) LCE_POOL_V4(true, unsigned, grid_for(n / 4, 256, 1 << 22));
-      else LCE_POOL_V4(false, unsigned, grid_for(n / 4, 256, 1 << 22));
+    dim3 grid((ow * C4 + 255) / 256, oh, d->batch);
+#define LCE_POOL_V4(MAXV, F)                                                                   \
+  pool_v4_kernel<MAXV, F><<<grid, 256, 0, as_stream(stream)>>>(                                \
+      reinterpret_cast<const float4*>(in), reinterpret_cast<float4*>(out), d->in_h, d->in_w,   \
+      C4, oh, ow, d->filter_h, d->filter_w, d->stride_h, d->stride_w, ph, pw, d->activation)
+    const int f = (d->filter_h == d->filter_w && (d->filter_h == 2 || d->filter_h == 3))
+                      ? d->filter_h : 0;
+    if (is_max) {
+      if (f == 2) LCE_POOL_V4(true, 2); else if (f == 3) LCE_POOL_V4(true, 3); else LCE_POOL_V4(true, 0);
     } else {
-      if (is_max) LCE_POOL_V4(true, long long, grid_for(n / 4, 256));
-      else LCE_POOL_V4(false, long long, grid_for(n / 4, 256));
+      if (f == 2) LCE_POOL_V4(false, 2); else if (f == 3) LCE_POOL_V4(false, 3); else LCE_POOL_V4(false, 0);
     }
 #undef LCE_POOL_V4
     return launch_check("pool_v4_kernel");
