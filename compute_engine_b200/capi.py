@@ -67,7 +67,7 @@ def lib():
     """Load liblce_b200.so (built in-tree). Fails loudly if it is missing."""
     global _lib
     if _lib is None:
-        path = _build.cuda_lib_path()
+        path = os.environ.get("LCE_B200_LIB") or _build.cuda_lib_path()   # override: A/B experiments
         if not os.path.exists(path):
             raise LceError(f"{path} is missing: run `python -c 'import __graft_entry__ as g; "
                            "g.build()'` (there is no CPU fallback)")
