@@ -5,11 +5,13 @@
 //                            tensorflow/lite/kernels/padding.h:32-82
 //   output-transform fold    LCE/tflite/kernels/bconv2d.cc:353-389 (in double, on the host)
 // and launches the kernels of lce_b200_kernels.cuh. There is no CPU compute path.
+#include <algorithm>
 #include <atomic>
 #include <climits>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -124,8 +126,43 @@ struct GemmCore {
   }
 };
 
+int sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
+      n = 148;
+  }
+  return n;
+}
+
 template <int V, int OUT>
 int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  // K in one chunk: persistent kernel (weights + epilogue vectors resident, two-stage
+  // gather ring); otherwise one CTA per tile with K staged chunk by chunk.
+  // MEASURED SLOWER than the one-shot kernel on every QuickNet layer (S1 0.193 -> 0.208 ms,
+  // S3 0.151 -> 0.181 ms, profiles/r01_persistent_experiment.txt): the four resident CTAs of an
+  // SM run in lock-step, so the inter-CTA overlap of gather / compute / epilogue phases that
+  // the hardware block scheduler gives the one-shot kernel for free is lost. Kept for
+  // experiments behind LCE_B200_PERSISTENT=1; off by default.
+  static const bool use_persistent = [] {
+    const char* e = getenv("LCE_B200_PERSISTENT");
+    return e && e[0] == '1';
+  }();
+  const size_t psmem = static_cast<size_t>(p.Kv) * (lce::kBN + 2 * lce::kBM) * V * 4;
+  if (use_persistent && p.n_chunks == 1 && psmem <= 80 * 1024) {
+    static bool pattr_set = false;
+    if (!pattr_set) {
+      CUDA_OK(cudaFuncSetAttribute(lce::bconv_persistent_kernel<V, OUT>,
+                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+      pattr_set = true;
+    }
+    const unsigned ctas = static_cast<unsigned>(sm_count() * lce::kCtasPerSm);
+    dim3 pgrid(std::max(1u, std::min(grid.x, ctas / std::max(1u, grid.y))), grid.y);
+    lce::bconv_persistent_kernel<V, OUT><<<pgrid, lce::kThreads, psmem, s>>>(p);
+    return launch_check("bconv_persistent_kernel");
+  }
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_OK(cudaFuncSetAttribute(lce::bconv_kernel<V, OUT>,

@@ -194,29 +194,13 @@ __device__ __forceinline__ int round_saturate_i8(float y) {
 // zero-filling 4V-byte cp.async (out-of-bounds taps read as 0 bits = +1, the
 // reference's one-padding: reference.h:106, optimized_bgemm.h:30-31).
 // ------------------------------------------------------------------------- //
-template <int V, int OUT>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvKParams p) {
-  using Vec = typename VecT<V>::T;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Vec* A_s = reinterpret_cast<Vec*>(smem_raw);     // [Kc_v][BM]
-  Vec* W_s = A_s + static_cast<size_t>(p.Kc_v) * kBM;  // [Kc_v][BN]
-  __shared__ __align__(8) uint64_t wbar;
+// ---- shared device functions of the one-shot and the persistent kernel ----------------
 
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int tn = lane & 7, tm = lane >> 3;
-  const int nt = blockIdx.y;
-  const int g = nt / p.tiles_per_group;
-  const int tg = nt - g * p.tiles_per_group;
-  const long long m0 = static_cast<long long>(blockIdx.x) * kBM;
-
-  if (tid == 0) {
-    mbar_init(&wbar, 1);
-    fence_barrier_init();
-  }
-  __syncthreads();
-
-  // ---- per-thread gather state: pixel `lp`, every second k-vector ---------
+// Gather one K chunk of the im2col rows of tile `m0` into A_buf[kv - kv0][pixel] with
+// zero-filling cp.async. Thread t handles pixel t % BM and every second k-vector.
+template <int V>
+__device__ __forceinline__ void gather_tile(const ConvKParams& p, typename VecT<V>::T* A_buf,
+                                            long long m0, int g, int kv0, int kv1, int tid) {
   const int lp = tid & (kBM - 1);
   const int half = tid / kBM;
   const long long gm = m0 + lp;
@@ -237,55 +221,38 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
     img = p.in + b * p.H * static_cast<long long>(p.W) * p.Cw_total +
           static_cast<long long>(g) * p.Cw_pg;
   }
-
-  int acc[kTM][kTN];
-#pragma unroll
-  for (int i = 0; i < kTM; ++i)
-#pragma unroll
-    for (int j = 0; j < kTN; ++j) acc[i][j] = 0;
-
-  uint32_t phase = 0;
-  for (int ch = 0; ch < p.n_chunks; ++ch) {
-    const int kv0 = ch * p.Kc_v;
-    const int kv1 = min(kv0 + p.Kc_v, p.Kv);
-    if (tid == 0) {
-      const uint32_t bytes = static_cast<uint32_t>(kv1 - kv0) * kBN * V * 4u;
-      mbar_arrive_expect_tx(&wbar, bytes);
-      bulk_g2s(W_s, p.wt + (static_cast<size_t>(nt) * p.Kv + kv0) * kBN * V, bytes, &wbar);
-    }
-    {
-      int kv = kv0 + half;
-      int tap = kv / p.CwV;
-      int cv = kv - tap * p.CwV;
-      int fy = tap / p.KW;
-      int fx = tap - fy * p.KW;
-      for (; kv < kv1; kv += 2) {
-        const int iy = iy0 + fy * p.dh;
-        const int ix = ix0 + fx * p.dw;
-        const bool inside = pix_valid && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
-                            static_cast<unsigned>(ix) < static_cast<unsigned>(p.W);
-        const int32_t* src =
-            inside ? img + (static_cast<long long>(iy) * p.W + ix) * p.Cw_total + cv * V : p.in;
-        cp_async_zfill<V * 4>(&A_s[static_cast<size_t>(kv - kv0) * kBM + lp], src,
-                              inside ? V * 4 : 0);
-        cv += 2;
-        while (cv >= p.CwV) {
-          cv -= p.CwV;
-          if (++fx == p.KW) {
-            fx = 0;
-            ++fy;
-          }
-        }
+  int kv = kv0 + half;
+  int tap = kv / p.CwV;
+  int cv = kv - tap * p.CwV;
+  int fy = tap / p.KW;
+  int fx = tap - fy * p.KW;
+  for (; kv < kv1; kv += 2) {
+    const int iy = iy0 + fy * p.dh;
+    const int ix = ix0 + fx * p.dw;
+    const bool inside = pix_valid && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
+                        static_cast<unsigned>(ix) < static_cast<unsigned>(p.W);
+    const int32_t* src =
+        inside ? img + (static_cast<long long>(iy) * p.W + ix) * p.Cw_total + cv * V : p.in;
+    cp_async_zfill<V * 4>(&A_buf[static_cast<size_t>(kv - kv0) * kBM + lp], src,
+                          inside ? V * 4 : 0);
+    cv += 2;
+    while (cv >= p.CwV) {
+      cv -= p.CwV;
+      if (++fx == p.KW) {
+        fx = 0;
+        ++fy;
       }
     }
-    cp_async_wait_all();
-    mbar_wait(&wbar, phase);
-    phase ^= 1u;
-    __syncthreads();
+  }
+}
 
+template <int V>
+__device__ __forceinline__ void compute_chunk(const typename VecT<V>::T* A_s,
+                                              const typename VecT<V>::T* W_s, int nkv, int warp,
+                                              int tm, int tn, int (&acc)[kTM][kTN]) {
+  using Vec = typename VecT<V>::T;
     const Vec* a_ptr = A_s + warp * 16 + tm;
     const Vec* w_ptr = W_s + tn;
-    const int nkv = kv1 - kv0;
     // Main loop: 8 K-words at a time through a carry-save adder tree, so that 8
     // XOR words cost 4 POPCs (XU pipe, 16/clk/SM) + 16 LOP3s (ALU pipe, 64/clk/SM)
     // instead of 8 POPCs -- the two pipes issue side by side (measured:
@@ -318,29 +285,32 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
 #pragma unroll
         for (int j = 0; j < kTN; ++j) acc[i][j] += xor_popc(a[i], w[j]);
     }
-    __syncthreads();
-  }
+}
 
-  // ------------------------------ epilogue --------------------------------
-  // Position j*8+tn of the weight tile holds channel tn*8+j, so each thread owns
-  // 8 CONSECUTIVE output channels and stores them with 128-bit writes.
+// Position j*8+tn of the weight tile holds channel tn*8+j, so each thread owns 8 CONSECUTIVE
+// output channels and stores them with 128-bit writes. mulp / biasp / thrp point at this
+// thread's first channel (global memory, or the persistent kernel's shared-memory copy).
+template <int OUT>
+__device__ __forceinline__ void epilogue_tile(const ConvKParams& p, int (&acc)[kTM][kTN],
+                                              long long m0, int g, int tg, int warp, int tm,
+                                              int tn, const float* mulp, const float* biasp,
+                                              const int32_t* thrp) {
   const int c_tile = g * p.cout_pg + tg * kBN;
   const int valid = min(kBN, p.cout_pg - tg * kBN);
   const int cofs = tn * 8;
   const int c0 = c_tile + cofs;
   const int taps = p.KH * p.KW;
-
   float mul_r[kTN], bias_r[kTN];
   int thr_r[kTN];
   if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_INT8) {
 #pragma unroll
     for (int j = 0; j < kTN; ++j) {
-      mul_r[j] = p.mul[c0 + j];
-      bias_r[j] = p.bias[c0 + j];
+      mul_r[j] = mulp[j];
+      bias_r[j] = biasp[j];
     }
   } else if (OUT == LCE_OUT_BITPACKED) {
 #pragma unroll
-    for (int j = 0; j < kTN; ++j) thr_r[j] = p.thr[c0 + j];
+    for (int j = 0; j < kTN; ++j) thr_r[j] = thrp[j];
   }
   const bool full = cofs + kTN <= valid;
 
@@ -483,6 +453,130 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
       }
     }
   }
+}
+
+// ------------------------------------------------------------------------- //
+// One-shot kernel: one CTA = one 64 x 64 tile, K staged chunk by chunk (any K).
+// ------------------------------------------------------------------------- //
+template <int V, int OUT>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvKParams p) {
+  using Vec = typename VecT<V>::T;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Vec* A_s = reinterpret_cast<Vec*>(smem_raw);     // [Kc_v][BM]
+  Vec* W_s = A_s + static_cast<size_t>(p.Kc_v) * kBM;  // [Kc_v][BN]
+  __shared__ __align__(8) uint64_t wbar;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tn = lane & 7, tm = lane >> 3;
+  const int nt = blockIdx.y;
+  const int g = nt / p.tiles_per_group;
+  const int tg = nt - g * p.tiles_per_group;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kBM;
+
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  int acc[kTM][kTN];
+#pragma unroll
+  for (int i = 0; i < kTM; ++i)
+#pragma unroll
+    for (int j = 0; j < kTN; ++j) acc[i][j] = 0;
+
+  uint32_t phase = 0;
+  for (int ch = 0; ch < p.n_chunks; ++ch) {
+    const int kv0 = ch * p.Kc_v;
+    const int kv1 = min(kv0 + p.Kc_v, p.Kv);
+    if (tid == 0) {
+      const uint32_t bytes = static_cast<uint32_t>(kv1 - kv0) * kBN * V * 4u;
+      mbar_arrive_expect_tx(&wbar, bytes);
+      bulk_g2s(W_s, p.wt + (static_cast<size_t>(nt) * p.Kv + kv0) * kBN * V, bytes, &wbar);
+    }
+    gather_tile<V>(p, A_s, m0, g, kv0, kv1, tid);
+    cp_async_wait_all();
+    mbar_wait(&wbar, phase);
+    phase ^= 1u;
+    __syncthreads();
+    compute_chunk<V>(A_s, W_s, kv1 - kv0, warp, tm, tn, acc);
+    __syncthreads();
+  }
+  const int c0 = g * p.cout_pg + tg * kBN + tn * 8;
+  epilogue_tile<OUT>(p, acc, m0, g, tg, warp, tm, tn, p.mul + c0, p.bias + c0, p.thr + c0);
+}
+
+// ------------------------------------------------------------------------- //
+// Persistent kernel (K fits one chunk): each CTA keeps its weight tile and epilogue
+// vectors in shared memory and walks over M tiles with a two-stage ring -- the patch
+// gather of tile t+1 (cp.async) is in flight while tile t is multiplied and stored,
+// so neither the gather latency nor the per-CTA set-up is paid per tile.
+// ------------------------------------------------------------------------- //
+template <int V, int OUT>
+__global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_persistent_kernel(const ConvKParams p) {
+  using Vec = typename VecT<V>::T;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  Vec* W_s = reinterpret_cast<Vec*>(smem_raw);                       // [Kv][BN]
+  Vec* A_s0 = W_s + static_cast<size_t>(p.Kv) * kBN;                 // [2][Kv][BM]
+  Vec* A_s1 = A_s0 + static_cast<size_t>(p.Kv) * kBM;
+  __shared__ __align__(16) float ep_mul[kBN];
+  __shared__ __align__(16) float ep_bias[kBN];
+  __shared__ __align__(16) int32_t ep_thr[kBN];
+  __shared__ __align__(8) uint64_t wbar;
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int tn = lane & 7, tm = lane >> 3;
+  const int nt = blockIdx.y;
+  const int g = nt / p.tiles_per_group;
+  const int tg = nt - g * p.tiles_per_group;
+  const long long m_tiles = (p.M + kBM - 1) / kBM;
+
+  if (tid == 0) {
+    mbar_init(&wbar, 1);
+    fence_barrier_init();
+    const uint32_t bytes = static_cast<uint32_t>(p.Kv) * kBN * V * 4u;
+    mbar_arrive_expect_tx(&wbar, bytes);
+    bulk_g2s(W_s, p.wt + static_cast<size_t>(nt) * p.Kv * kBN * V, bytes, &wbar);
+  }
+  if (tid < kBN) {
+    const int c = g * p.cout_pg + tg * kBN + tid;
+    if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_INT8) {
+      ep_mul[tid] = p.mul[c];
+      ep_bias[tid] = p.bias[c];
+    } else if (OUT == LCE_OUT_BITPACKED) {
+      ep_thr[tid] = p.thr[c];
+    }
+  }
+  long long t = blockIdx.x;
+  if (t < m_tiles) gather_tile<V>(p, A_s0, t * kBM, g, 0, p.Kv, tid);
+  asm volatile("cp.async.commit_group;" ::: "memory");
+  __syncthreads();          // mbarrier init + epilogue vectors visible
+  mbar_wait(&wbar, 0);      // weights have landed
+
+  int buf = 0;
+  for (; t < m_tiles; t += gridDim.x, buf ^= 1) {
+    Vec* A_cur = buf ? A_s1 : A_s0;
+    Vec* A_nxt = buf ? A_s0 : A_s1;
+    const long long tn_ = t + gridDim.x;
+    // the other buffer was last read by compute(t - 1); the barrier after that compute
+    // (below) makes it safe to refill now
+    if (tn_ < m_tiles) gather_tile<V>(p, A_nxt, tn_ * kBM, g, 0, p.Kv, tid);
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's gather is complete
+    __syncthreads();
+    int acc[kTM][kTN];
+#pragma unroll
+    for (int i = 0; i < kTM; ++i)
+#pragma unroll
+      for (int j = 0; j < kTN; ++j) acc[i][j] = 0;
+    compute_chunk<V>(A_cur, W_s, p.Kv, warp, tm, tn, acc);
+    __syncthreads();          // everyone is done reading A_cur
+    epilogue_tile<OUT>(p, acc, t * kBM, g, tg, warp, tm, tn, ep_mul + tn * 8, ep_bias + tn * 8,
+                       ep_thr + tn * 8);
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
 }
 
 // Re-lay the OHWI-packed filter [cout][taps][Cw_pg] into the kernel's tiles:
