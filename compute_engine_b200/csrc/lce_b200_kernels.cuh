@@ -486,6 +486,18 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
 #pragma unroll
     for (int j = 0; j < kTN; ++j) acc[i][j] = 0;
 
+  // Fused shortcut: start pulling this thread's residual values towards L2 now, so the
+  // DRAM latency of the epilogue's loads is covered by the gather + inner product.
+  if (OUT == LCE_OUT_FLOAT && p.residual != nullptr) {
+#pragma unroll
+    for (int i = 0; i < kTM; ++i) {
+      const long long m = m0 + warp * 16 + i * 4 + tm;
+      if (m < p.M)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + m * p.cout + g * p.cout_pg +
+                                                       tg * kBN + tn * 8));
+    }
+  }
+
   uint32_t phase = 0;
   for (int ch = 0; ch < p.n_chunks; ++ch) {
     const int kv0 = ch * p.Kc_v;
