@@ -9,6 +9,7 @@
 #include <cfloat>
 #include <climits>
 #include <cstdint>
+#include <cstdlib>
 
 #include "lce_b200_builtins.h"
 
@@ -614,11 +615,27 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   const long long M = static_cast<long long>(g.B) * g.OH * g.OW;
   if (M == 0) return 0;
   const int K = g.KH * g.KW * g.Cin;
-  if (K <= kDirectMaxK && g.Cout <= kDirectMaxCout && !((uintptr_t)out & 15) &&
-      M * ((g.Cout + 15) / 16) < (1LL << 30)) {
-    const int G = (g.Cout + 15) / 16;
+  // experiments: LCE_B200_DIRECT_MAXK overrides the small-K threshold of the direct kernel
+  static const int direct_max_k = [] {
+    const char* e = getenv("LCE_B200_DIRECT_MAXK");
+    return e ? atoi(e) : kDirectMaxK;
+  }();
+  const int Gd = (g.Cout + 15) / 16;
+  const size_t direct_smem =
+      (static_cast<size_t>(K) * Gd * kDirectGroupStride + Gd * 16) * sizeof(float);
+  if (K <= direct_max_k && g.Cout <= kDirectMaxCout && !((uintptr_t)out & 15) &&
+      M * Gd < (1LL << 30) && direct_smem <= 96 * 1024) {
+    const int G = Gd;
     const long long threads = M * G;
-    const size_t smem = (static_cast<size_t>(K) * G * kDirectGroupStride + G * 16) * sizeof(float);
+    const size_t smem = direct_smem;
+    if (smem > 48 * 1024) {
+      static bool attr = false;
+      if (!attr) {
+        cudaFuncSetAttribute(conv_direct16_kernel<0, 0, 0>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr = true;
+      }
+    }
     // 128 threads = (128 / G) pixels x G groups, kPX pixels each
     const int px_per_blk = 128 / G;
     const unsigned blocks = static_cast<unsigned>((M + px_per_blk * kPX - 1) / (px_per_blk * kPX));

@@ -290,3 +290,30 @@ def test_bgemm_large_linearity_properties(capi):
     rows = [0, 1, 1023, 2047]
     want = L.bgemm(A[rows].cpu().numpy(), W.cpu().numpy(), threads=4)
     assert np.array_equal(acc[rows].cpu().numpy(), want)
+
+
+def test_bconv_fused_residual_and_pack_entry_point(capi):
+    """lce_b200_bconv2d_run_fused == LceBconv2d -> ADD(shortcut) -> LceQuantize, bit for bit."""
+    import ctypes as C
+    rng = np.random.default_rng(5)
+    for (b, hw, c, co, act_add) in [(2, 14, 64, 64, L.ACT_NONE), (1, 7, 512, 128, L.ACT_RELU),
+                                    (3, 9, 96, 72, L.ACT_NONE)]:
+        case = L.make_bconv_case(60 + c, b, hw, hw, c, 3, 3, co, activation=L.ACT_RELU)
+        res = rng.standard_normal((b, hw, hw, co)).astype(np.float32)
+        plan = capi.BConv2d(gpu_desc(capi, case.desc), case.filt, case.mul, case.bias)
+        out = torch.empty((b, hw, hw, co), device="cuda")
+        packed = torch.empty((b, hw, hw, L.cdiv(co, 32)), dtype=torch.int32, device="cuda")
+        d_in, d_res = dev(case.inp), dev(res)          # keep the device tensors alive
+        rc = capi.lib().lce_b200_bconv2d_run_fused(
+            plan._h, C.c_void_p(d_in.data_ptr()), C.c_void_p(d_res.data_ptr()),
+            C.c_int(act_add), C.c_void_p(out.data_ptr()), C.c_void_p(packed.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, capi.lib().lce_b200_last_error()
+        y = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias)
+        want = (y + res).astype(np.float32)
+        if act_add == L.ACT_RELU:
+            want = np.maximum(want, 0)
+        torch.cuda.synchronize()
+        assert_same_bits(out.cpu().numpy(), want, "fused sum")
+        assert_same_bits(packed.cpu().numpy(), L.quantize(want), "fused packed signs")
+        plan.close()
