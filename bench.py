@@ -163,6 +163,24 @@ def make_stage_inputs(batch, seed):
     return [rng.standard_normal((batch, hw, hw, c), dtype=np.float32) for (hw, c) in STAGES]
 
 
+def ncu_traffic_per_launch():
+    """Mean dram__bytes_read + dram__bytes_write per lce::bconv_kernel launch from the committed
+    `ncu --set full` capture of this same command (profiles/r01_ncu_bconv_fused_final_summary.csv:
+    the 16 LceBconv2d launches of one QuickNet step), or None."""
+    import csv
+    path = os.path.join(REPO, "profiles", "r01_ncu_bconv_fused_final_summary.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units = rows[0], rows[1]
+        ir, iw = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+        scale = {"Mbyte": 1e6, "Kbyte": 1e3, "Gbyte": 1e9, "byte": 1.0}
+        tot = [float(r[ir]) * scale.get(units[ir], 1.0) + float(r[iw]) * scale.get(units[iw], 1.0)
+               for r in rows[2:]]
+        return sum(tot) / len(tot) if tot else None
+    except Exception:
+        return None
+
+
 def bconv_alg_bytes(in_shape, filt_shape, out_shape, out_itemsize=4):
     """packed input + packed filter + output + multiplier/bias."""
     return (int(np.prod(in_shape)) * 4 + int(np.prod(filt_shape)) * 4 +
@@ -585,7 +603,11 @@ def main_b200(args):
             "gpu_launches": launches,
             "roofline": {"kernel": "lce::bconv_kernel (LceBconv2d)", "bound": "hbm",
                          "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
+                         "frac": achieved / hbm_peak, "peak_source": peak_src,
+                         "traffic": ncu_traffic_per_launch() if args.workload == "quicknet" else None,
+                         "traffic_unit": "bytes per launch (mean of the 16 launches of one step, "
+                                         "ncu --set full, profiles/r01_ncu_bconv_fused_final_summary.csv)",
+                         "alg_bytes_per_launch": r["conv_bytes"] / max(r["n_conv"] // K, 1),
                          "launches_timed": r["n_conv"],
                          "avg_launch_ms": r["conv_s_per_step"] * 1e3 * K / max(r["n_conv"], 1),
                          "share_of_step": r["conv_share"], "timing": r["timing_note"],

@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restr
 // ---- plain-GEMM convolution (1x1, stride 1: A = [M, K] row-major): 128x128x16 tiles, 8x8
 // outputs per thread, 128-bit global loads along K, register-prefetch double buffering ----
 constexpr int kPM = 128, kPN = 128, kPK = 16;
-__global__ void __launch_bounds__(256) conv_gemm128_kernel(const float* __restrict__ A,
+__global__ void __launch_bounds__(256, 2) conv_gemm128_kernel(const float* __restrict__ A,
                                                            const float* __restrict__ Wt,
                                                            const float* __restrict__ bias,
                                                            float* __restrict__ out, long long M,
