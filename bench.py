@@ -334,7 +334,7 @@ def graph_workload(args, D):
         D.dist.broadcast(model, src=0)     # packed weights + graph; the only collective
     model_bytes = model.cpu().numpy().tobytes()
     g = H.HostGraph.from_tflite(model_bytes, device_arena=True)
-    fused = 0 if os.environ.get("LCE_NO_FUSION") else g.fuse_residual_blocks()
+    fused = 0 if os.environ.get("LCE_NO_FUSION") else g.fuse_all()
     t_in, t_out = g.inputs()[0], g.outputs()[0]
     g.resize_input(t_in, (B, 224, 224, 3))
     g.allocate_tensors()

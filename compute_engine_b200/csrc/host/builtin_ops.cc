@@ -173,6 +173,58 @@ TfLiteStatus PoolInvoke(TfLiteContext* c, TfLiteNode* n) {
   return kTfLiteOk;
 }
 
+// ------------- fused MAX_POOL_2D(2x2 s1 VALID) + DEPTHWISE_CONV_2D(3x3) ------------- //
+// Created by Graph::FuseFloatGlue; builtin_data = { BuiltinParams pool, BuiltinParams dw }.
+struct PoolDwParams {
+  BuiltinParams pool, dw;
+};
+void* PoolDwInit(TfLiteContext*, const char* buffer, size_t length) {
+  auto* p = new PoolDwParams();
+  memset(p, 0, sizeof(*p));
+  if (buffer && length >= sizeof(PoolDwParams)) memcpy(p, buffer, sizeof(PoolDwParams));
+  return p;
+}
+void PoolDwFree(TfLiteContext*, void* p) { delete static_cast<PoolDwParams*>(p); }
+bool PoolDwDescs(TfLiteContext* c, TfLiteNode* n, lce_f32_pool_desc* pd, lce_f32_conv_desc* dd) {
+  const auto& pp = *static_cast<PoolDwParams*>(n->user_data);
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* f = T(c, n->inputs, 1);
+  if (!in || !f || in->dims->size != 4 || f->dims->size != 4) return false;
+  pd->batch = in->dims->data[0]; pd->in_h = in->dims->data[1]; pd->in_w = in->dims->data[2];
+  pd->channels = in->dims->data[3];
+  pd->filter_h = pp.pool.filter_h; pd->filter_w = pp.pool.filter_w;
+  pd->stride_h = pp.pool.stride_h; pd->stride_w = pp.pool.stride_w;
+  pd->padding = pp.pool.padding; pd->activation = pp.pool.activation;
+  int ph, pw;
+  if (lce_b200_f32_pool_out_shape(pd, &ph, &pw)) return false;
+  dd->batch = pd->batch; dd->in_h = ph; dd->in_w = pw; dd->in_c = pd->channels;
+  dd->filter_h = f->dims->data[1]; dd->filter_w = f->dims->data[2]; dd->out_c = f->dims->data[3];
+  dd->stride_h = pp.dw.stride_h; dd->stride_w = pp.dw.stride_w;
+  dd->dilation_h = pp.dw.dilation_h; dd->dilation_w = pp.dw.dilation_w;
+  dd->padding = pp.dw.padding; dd->activation = pp.dw.activation;
+  return true;
+}
+TfLiteStatus PoolDwPrepare(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_pool_desc pd;
+  lce_f32_conv_desc dd;
+  B_ENSURE(c, PoolDwDescs(c, n, &pd, &dd), "MAX_POOL_2D+DEPTHWISE_CONV_2D: bad shapes");
+  int oh, ow;
+  B_CAPI(c, lce_b200_f32_conv_out_shape(&dd, &oh, &ow));
+  return Resize(c, T(c, n->outputs, 0), {dd.batch, oh, ow, dd.out_c});
+}
+TfLiteStatus PoolDwInvoke(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_pool_desc pd;
+  lce_f32_conv_desc dd;
+  PoolDwDescs(c, n, &pd, &dd);
+  const TfLiteTensor* bias = T(c, n->inputs, 2);
+  B_CAPI(c, lce_b200_f32_maxpool2x2_depthwise3x3(&pd, &dd, T(c, n->inputs, 0)->data.f,
+                                                   T(c, n->inputs, 1)->data.f,
+                                                   bias ? bias->data.f : nullptr,
+                                                   T(c, n->outputs, 0)->data.f,
+                                                   lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
 // ------------------------------ ADD / MUL / RELU ------------------------------ //
 TfLiteStatus EltPrepare(TfLiteContext* c, TfLiteNode* n) {
   const TfLiteTensor* a = T(c, n->inputs, 0);
@@ -279,6 +331,11 @@ TfLiteStatus ReshapeInvoke(TfLiteContext* c, TfLiteNode* n) {
 }
 
 }  // namespace
+
+const TfLiteRegistration* FusedPoolDepthwiseRegistration() {
+  static TfLiteRegistration r = {PoolDwInit, PoolDwFree, PoolDwPrepare, PoolDwInvoke};
+  return &r;
+}
 
 void RegisterBuiltinOps(OpResolver* r) {
   static TfLiteRegistration conv = {Init, Free, ConvPrepare<false>, ConvInvoke<false>};

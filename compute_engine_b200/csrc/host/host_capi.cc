@@ -100,6 +100,7 @@ int lce_host_enable_cuda_graph(void* g, int on) {
   return static_cast<Graph*>(g)->EnableCudaGraph(on != 0);
 }
 int lce_host_fuse_residual_blocks(void* g) { return static_cast<Graph*>(g)->FuseResidualBlocks(); }
+int lce_host_fuse_float_glue(void* g) { return static_cast<Graph*>(g)->FuseFloatGlue(); }
 void lce_host_enable_profiling(void* g, int on) { static_cast<Graph*>(g)->EnableProfiling(on != 0); }
 void lce_host_reset_profile(void* g) { static_cast<Graph*>(g)->ResetProfile(); }
 double lce_host_node_time_ms(void* g, int node) { return static_cast<Graph*>(g)->NodeTimeMs(node); }

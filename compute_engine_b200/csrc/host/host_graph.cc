@@ -380,6 +380,64 @@ int Graph::FuseResidualBlocks() {
   return removed;
 }
 
+const TfLiteRegistration* FusedPoolDepthwiseRegistration();  // builtin_ops.cc
+
+int Graph::FuseFloatGlue() {
+  if (!device_arena_) return 0;
+  int removed = 0;
+  for (size_t i = 0; i < nodes_.size(); ++i) {
+    NodeRecord& pool = *nodes_[i];
+    if (pool.name != "builtin:17" || pool.initialized ||
+        pool.builtin_blob.size() < sizeof(BuiltinParams))
+      continue;
+    const auto* pp = reinterpret_cast<const BuiltinParams*>(pool.builtin_blob.data());
+    if (pp->filter_h != 2 || pp->filter_w != 2 || pp->stride_h != 1 || pp->stride_w != 1 ||
+        pp->padding != 1 /* VALID */ || pp->activation != 0)
+      continue;
+    const int y = pool.node.outputs->data[0];
+    if (std::find(outputs_.begin(), outputs_.end(), y) != outputs_.end()) continue;
+    size_t di = nodes_.size();
+    int n_cons = 0;
+    for (size_t k = 0; k < nodes_.size(); ++k)
+      for (int q = 0; q < nodes_[k]->node.inputs->size; ++q)
+        if (nodes_[k]->node.inputs->data[q] == y) { ++n_cons; di = k; }
+    if (n_cons != 1 || di <= i) continue;
+    NodeRecord& dw = *nodes_[di];
+    if (dw.name != "builtin:4" || dw.node.inputs->data[0] != y ||
+        dw.builtin_blob.size() < sizeof(BuiltinParams))
+      continue;
+    const auto* dp = reinterpret_cast<const BuiltinParams*>(dw.builtin_blob.data());
+    const TfLiteTensor& f = tensors_[dw.node.inputs->data[1]];
+    if (f.dims->size != 4 || f.dims->data[1] != 3 || f.dims->data[2] != 3 ||
+        (f.dims->data[3] & 3) || dp->dilation_h != 1 || dp->dilation_w != 1 ||
+        dp->depth_multiplier != 1 || tensors_[y].type != kTfLiteFloat32)
+      continue;
+    // rewrite the pool node into the fused node; it takes the depthwise node's constants / output
+    std::vector<uint8_t> blob(2 * sizeof(BuiltinParams));
+    memcpy(blob.data(), pp, sizeof(BuiltinParams));
+    memcpy(blob.data() + sizeof(BuiltinParams), dp, sizeof(BuiltinParams));
+    std::vector<int> ins{pool.node.inputs->data[0], dw.node.inputs->data[1],
+                         dw.node.inputs->size > 2 ? dw.node.inputs->data[2] : -1};
+    std::vector<int> outs{dw.node.outputs->data[0]};
+    LceB200IntArrayFree(pool.node.inputs);
+    LceB200IntArrayFree(pool.node.outputs);
+    pool.node.inputs = MakeDims(ins);
+    pool.node.outputs = MakeDims(outs);
+    pool.builtin_blob = blob;
+    pool.node.builtin_data = pool.builtin_blob.data();
+    pool.registration = FusedPoolDepthwiseRegistration();
+    pool.name = "MAX_POOL_2D+DEPTHWISE_CONV_2D";
+    LceB200IntArrayFree(dw.node.inputs);
+    LceB200IntArrayFree(dw.node.outputs);
+    LceB200IntArrayFree(dw.node.temporaries);
+    LceB200IntArrayFree(dw.node.intermediates);
+    nodes_.erase(nodes_.begin() + di);
+    ++removed;
+  }
+  allocated_ = false;
+  return removed;
+}
+
 TfLiteStatus Graph::AllocateTensors() {
   RefreshContext();
   if (graph_exec_) {

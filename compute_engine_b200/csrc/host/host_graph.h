@@ -73,6 +73,11 @@ class Graph {
   // Returns the number of (ADD, LceQuantize) nodes removed. Call before AllocateTensors.
   int FuseResidualBlocks();
 
+  // Fusions among the float builtins around the binary path:
+  //   MAX_POOL_2D(2x2, stride 1, VALID) -> DEPTHWISE_CONV_2D(3x3)  =>  one node
+  // (QuickNet's anti-aliased down-sampling). Bit-identical. Returns the nodes removed.
+  int FuseFloatGlue();
+
   // init (first time) + prepare of every node in order, then arena allocation.
   TfLiteStatus AllocateTensors();
   TfLiteStatus ResizeInputTensor(int tensor, const std::vector<int>& dims);

@@ -486,6 +486,62 @@ __global__ void __launch_bounds__(256) pool_v4_kernel(const float4* __restrict__
                   apply_act(v.w, act));
 }
 
+// max-pool 2x2 / stride 1 / VALID fused into the depthwise 3x3 that consumes it: one thread =
+// one output pixel x 4 channels; the 4x4 input window is loaded once (16 x LDG.128), the nine
+// pooled values are formed in registers and multiplied in the same (fy, fx) order as
+// depthwise_v4_kernel, so the result is bit-identical to the two-kernel sequence.
+__global__ void __launch_bounds__(256) pool2_dw3_v4_kernel(const float4* __restrict__ in,
+                                                           const float4* __restrict__ filter,
+                                                           const float4* __restrict__ bias,
+                                                           float4* __restrict__ out, int H, int W,
+                                                           int C4, int PH, int PW, int OH, int OW,
+                                                           int sh, int sw, int ph, int pw, int act) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= OW * C4) return;
+  const int ox = i / C4, c = i - ox * C4;
+  const int oy = blockIdx.y;
+  const long long b = blockIdx.z;
+  const int y0 = oy * sh - ph, x0 = ox * sw - pw;   // top-left pooled coordinate of the window
+  const float4* img = in + b * H * W * C4 + c;
+  const float4 lowest = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+  float4 v[4][4];
+#pragma unroll
+  for (int dy = 0; dy < 4; ++dy)
+#pragma unroll
+    for (int dx = 0; dx < 4; ++dx) {
+      const int y = y0 + dy, x = x0 + dx;
+      const bool ok = static_cast<unsigned>(y) < static_cast<unsigned>(H) &&
+                      static_cast<unsigned>(x) < static_cast<unsigned>(W);
+      v[dy][dx] = ok ? __ldg(img + (static_cast<long long>(y) * W + x) * C4) : lowest;
+    }
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int fy = 0; fy < 3; ++fy) {
+    const int py = y0 + fy;
+    if (static_cast<unsigned>(py) >= static_cast<unsigned>(PH)) continue;
+#pragma unroll
+    for (int fx = 0; fx < 3; ++fx) {
+      const int px = x0 + fx;
+      if (static_cast<unsigned>(px) >= static_cast<unsigned>(PW)) continue;
+      // pool_v4_kernel's order: (y, x), (y, x+1), (y+1, x), (y+1, x+1)
+      float4 m = lowest;
+      const float4 e0 = v[fy][fx], e1 = v[fy][fx + 1], e2 = v[fy + 1][fx], e3 = v[fy + 1][fx + 1];
+      m.x = fmaxf(fmaxf(fmaxf(fmaxf(m.x, e0.x), e1.x), e2.x), e3.x);
+      m.y = fmaxf(fmaxf(fmaxf(fmaxf(m.y, e0.y), e1.y), e2.y), e3.y);
+      m.z = fmaxf(fmaxf(fmaxf(fmaxf(m.z, e0.z), e1.z), e2.z), e3.z);
+      m.w = fmaxf(fmaxf(fmaxf(fmaxf(m.w, e0.w), e1.w), e2.w), e3.w);
+      const float4 w = __ldg(filter + (fy * 3 + fx) * C4 + c);
+      acc.x = fmaf(m.x, w.x, acc.x); acc.y = fmaf(m.y, w.y, acc.y);
+      acc.z = fmaf(m.z, w.z, acc.z); acc.w = fmaf(m.w, w.w, acc.w);
+    }
+  }
+  float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bb = __ldg(bias + c);
+  out[((b * OH + oy) * OW + ox) * C4 + c] =
+      make_float4(apply_act(acc.x + bb.x, act), apply_act(acc.y + bb.y, act),
+                  apply_act(acc.z + bb.z, act), apply_act(acc.w + bb.w, act));
+}
+
 template <bool MAX>
 __global__ void __launch_bounds__(256) pool_kernel(const float* __restrict__ in,
                                                    float* __restrict__ out, int B, int H, int W,
@@ -746,6 +802,34 @@ static bool vec4_ok(const void* a, const void* b, const void* o, int64_t n, int6
   return b_len == n && (n & 3) == 0 && !((uintptr_t)a & 15) && !((uintptr_t)b & 15) &&
          !((uintptr_t)o & 15);
 }
+int lce_b200_f32_maxpool2x2_depthwise3x3(const lce_f32_pool_desc* pool, const lce_f32_conv_desc* dw,
+                                         const float* in, const float* filter, const float* bias,
+                                         float* out, void* stream) {
+  int ph_, pw_;
+  if (lce_b200_f32_pool_out_shape(pool, &ph_, &pw_)) return 1;
+  if (pool->filter_h != 2 || pool->filter_w != 2 || pool->stride_h != 1 || pool->stride_w != 1 ||
+      pool->padding != LCE_PADDING_VALID || pool->activation != LCE_ACT_NONE)
+    return fail("maxpool2x2_depthwise3x3: the pool must be 2x2, stride 1, VALID, no activation");
+  ConvGeom g;
+  if (make_geom(dw, &g)) return 1;
+  if (dw->filter_h != 3 || dw->filter_w != 3 || dw->dilation_h != 1 || dw->dilation_w != 1 ||
+      dw->out_c != dw->in_c || (dw->in_c & 3) || dw->in_c != pool->channels ||
+      dw->in_h != ph_ || dw->in_w != pw_ || dw->batch != pool->batch)
+    return fail("maxpool2x2_depthwise3x3: unsupported depthwise shape");
+  if (((uintptr_t)in & 15) || ((uintptr_t)filter & 15) || ((uintptr_t)out & 15) ||
+      ((uintptr_t)bias & 15) || g.B > 65535 || g.OH > 65535)
+    return fail("maxpool2x2_depthwise3x3: unaligned pointers or too many rows");
+  const long long n = static_cast<long long>(g.B) * g.OH * g.OW * g.Cout;
+  if (n == 0) return 0;
+  const int C4 = g.Cout >> 2;
+  dim3 grid((g.OW * C4 + 255) / 256, g.OH, g.B);
+  pool2_dw3_v4_kernel<<<grid, 256, 0, as_stream(stream)>>>(
+      reinterpret_cast<const float4*>(in), reinterpret_cast<const float4*>(filter),
+      reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), pool->in_h,
+      pool->in_w, C4, ph_, pw_, g.OH, g.OW, g.sh, g.sw, g.ph, g.pw, g.act);
+  return launch_check("pool2_dw3_v4_kernel");
+}
+
 int lce_b200_f32_add(const float* a, const float* b, float* out, int64_t n, int64_t b_len,
                      int act, void* stream) {
   if (n <= 0) return 0;

@@ -169,6 +169,13 @@ class HostGraph:
         """LceBconv2d -> ADD [-> LceQuantize] => one node. Call before allocate_tensors."""
         return lib().lce_host_fuse_residual_blocks(self._g)
 
+    def fuse_float_glue(self):
+        """MAX_POOL_2D(2x2 s1 VALID) -> DEPTHWISE_CONV_2D(3x3) => one node."""
+        return lib().lce_host_fuse_float_glue(self._g)
+
+    def fuse_all(self):
+        return self.fuse_residual_blocks() + self.fuse_float_glue()
+
     # ---- profiling / async IO (bench.py) ----
     def enable_profiling(self, on=True):
         lib().lce_host_enable_profiling(self._g, 1 if on else 0)

@@ -48,6 +48,14 @@ int lce_b200_f32_max_pool(const lce_f32_pool_desc* d, const float* in_dev, float
                           void* stream);
 int lce_b200_f32_avg_pool(const lce_f32_pool_desc* d, const float* in_dev, float* out_dev,
                           void* stream);
+/* Fused MAX_POOL_2D(2x2, stride 1, VALID) -> DEPTHWISE_CONV_2D(3x3, depth_multiplier 1): the
+ * anti-aliased down-sampling pair of QuickNet's transition blocks in one pass over the input
+ * (the pooled tensor never reaches HBM). `pool` describes the max-pool on the input, `dw` the
+ * depthwise conv on the POOLED tensor (dw->in_h / in_w = pooled size). channels % 4 == 0.
+ * Bit-identical to running the two kernels one after the other. */
+int lce_b200_f32_maxpool2x2_depthwise3x3(const lce_f32_pool_desc* pool, const lce_f32_conv_desc* dw,
+                                         const float* in_dev, const float* filter_dev,
+                                         const float* bias_dev, float* out_dev, void* stream);
 /* out[i] = act(a[i] (op) b[i % b_len]); b_len == n (same shape) or the last dim. */
 int lce_b200_f32_add(const float* a_dev, const float* b_dev, float* out_dev, int64_t n,
                      int64_t b_len, int activation, void* stream);

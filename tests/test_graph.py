@@ -199,6 +199,11 @@ def test_residual_block_fusion_rewrites_the_graph():
     assert names.count("LceQuantize") == 4             # first block of each stage
     assert "builtin:0" not in names and "LceBconv2d" not in names
     assert g.fuse_residual_blocks() == 0               # idempotent
+    # float glue: the three (max-pool 2x2 s1 -> blur depthwise 3x3 s2) pairs of the transitions
+    assert g.fuse_float_glue() == 3 and g.num_nodes() == 33
+    names = [g.node_name(i) for i in range(g.num_nodes())]
+    assert names.count("MAX_POOL_2D+DEPTHWISE_CONV_2D") == 3 and "builtin:17" not in names
+    assert names.count("builtin:4") == 1               # the stem's depthwise stays
     g.close()
 
 
@@ -212,6 +217,7 @@ def test_gpu_fused_graph_is_bit_identical_to_unfused(family):
         g = H.HostGraph.from_tflite(blob, device_arena=True)
         if fuse:
             assert g.fuse_residual_blocks() > 0
+            assert g.fuse_float_glue() == (3 if family == "quicknet" else 0)
         g.resize_input(g.inputs()[0], x.shape)
         g.allocate_tensors()
         g.enable_cuda_graph(True)

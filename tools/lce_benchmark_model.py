@@ -47,7 +47,7 @@ def main():
         ap.error("--graph or --zoo is required")
     t0 = time.perf_counter()
     g = H.HostGraph.from_tflite(blob, device_arena=True)
-    fused = g.fuse_residual_blocks() if a.fuse else 0
+    fused = g.fuse_all() if a.fuse else 0
     for t in g.inputs():
         shape = list(g.shape(t))
         shape[0] = a.batch
