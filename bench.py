@@ -552,7 +552,7 @@ def bgemm_sweep(args, D):
                              "binary_TOPS": round(2 * M * N * Kb / ms / 1e9, 2),
                              "alg_GBps": round(alg / ms / 1e6, 1),
                              "hbm_frac": round(alg / ms / 1e6 / (hbm_peak * D.world), 4),
-                             "popc_frac": round(M * N * Kw / ms / 1e3 /
+                             "popc_frac": round(M * N * Kw / ms * 1e3 /
                                                 (148 * 16 * sm_max * 1e6 * D.world), 3)})
                 gemm.close()
                 if D.rank == 0:

@@ -330,6 +330,102 @@ TfLiteStatus ReshapeInvoke(TfLiteContext* c, TfLiteNode* n) {
   return kTfLiteOk;
 }
 
+// ------------------------------- PAD / PADV2 ------------------------------- //
+// inputs: [x, paddings int32 [rank,2] (host constant), (PADV2: constant value, host scalar)].
+// float32 and int32 (bitpacked) tensors of rank <= 4 (TF/lite/kernels/pad.cc).
+bool PadGeometry(TfLiteContext* c, TfLiteNode* n, int32_t in4[4], int32_t before[4],
+                 int32_t after[4], int* rank) {
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* pads = T(c, n->inputs, 1);
+  if (!in || !pads || pads->type != kTfLiteInt32 || OnDevice(pads->data.raw) || !pads->data.raw)
+    return false;
+  const int r = in->dims->size;
+  if (r < 1 || r > 4 || Count(pads) != 2 * r) return false;
+  for (int i = 0; i < 4; ++i) { in4[i] = 1; before[i] = after[i] = 0; }
+  for (int i = 0; i < r; ++i) {
+    in4[4 - r + i] = in->dims->data[i];
+    before[4 - r + i] = pads->data.i32[2 * i];
+    after[4 - r + i] = pads->data.i32[2 * i + 1];
+    if (before[4 - r + i] < 0 || after[4 - r + i] < 0) return false;
+  }
+  *rank = r;
+  return true;
+}
+TfLiteStatus PadPrepare(TfLiteContext* c, TfLiteNode* n) {
+  int32_t in4[4], before[4], after[4];
+  int r = 0;
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  B_ENSURE(c, in && (in->type == kTfLiteFloat32 || in->type == kTfLiteInt32),
+           "PAD: only float32 / int32 tensors are supported");
+  B_ENSURE(c, PadGeometry(c, n, in4, before, after, &r),
+           "PAD: paddings must be a constant int32 [rank, 2] tensor with rank <= 4");
+  TfLiteIntArray* dims = LceB200IntArrayCreate(r);
+  for (int i = 0; i < r; ++i) dims->data[i] = in4[4 - r + i] + before[4 - r + i] + after[4 - r + i];
+  return c->ResizeTensor(c, T(c, n->outputs, 0), dims);
+}
+TfLiteStatus PadInvoke(TfLiteContext* c, TfLiteNode* n) {
+  int32_t in4[4], before[4], after[4];
+  int r = 0;
+  B_ENSURE(c, PadGeometry(c, n, in4, before, after, &r), "PAD: bad paddings");
+  uint32_t fill = 0;  // 0.0f / bitpacked +1
+  const TfLiteTensor* v = T(c, n->inputs, 2);
+  if (v) {
+    B_ENSURE(c, v->data.raw && !OnDevice(v->data.raw) && Count(v) == 1 && v->bytes == 4,
+             "PADV2: constant_values must be a constant 32-bit scalar");
+    memcpy(&fill, v->data.raw, 4);
+  }
+  B_CAPI(c, lce_b200_pad4d_32(T(c, n->inputs, 0)->data.raw, T(c, n->outputs, 0)->data.raw, in4,
+                              before, after, fill, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
+// ------------------------------ CONCATENATION ------------------------------ //
+// Strided device copies (one cudaMemcpy2DAsync per input): no kernel of ours.
+TfLiteStatus ConcatPrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  B_ENSURE(c, a && n->inputs->size >= 1, "CONCATENATION: no inputs");
+  const int r = a->dims->size;
+  int axis = P(n).axis < 0 ? P(n).axis + r : P(n).axis;
+  B_ENSURE(c, axis >= 0 && axis < r, "CONCATENATION: axis out of range");
+  B_ENSURE(c, P(n).activation == 0, "CONCATENATION: fused activation is not supported");
+  int sum = 0;
+  for (int k = 0; k < n->inputs->size; ++k) {
+    const TfLiteTensor* t = T(c, n->inputs, k);
+    B_ENSURE(c, t && t->dims->size == r && t->type == a->type,
+             "CONCATENATION: inputs must agree in rank and type");
+    for (int i = 0; i < r; ++i)
+      B_ENSURE(c, i == axis || t->dims->data[i] == a->dims->data[i],
+               "CONCATENATION: inputs must agree outside the axis");
+    sum += t->dims->data[axis];
+  }
+  TfLiteIntArray* dims = LceB200IntArrayCreate(r);
+  for (int i = 0; i < r; ++i) dims->data[i] = i == axis ? sum : a->dims->data[i];
+  return c->ResizeTensor(c, T(c, n->outputs, 0), dims);
+}
+TfLiteStatus ConcatInvoke(TfLiteContext* c, TfLiteNode* n) {
+  TfLiteTensor* out = T(c, n->outputs, 0);
+  const int r = out->dims->size;
+  const int axis = P(n).axis < 0 ? P(n).axis + r : P(n).axis;
+  size_t outer = 1, inner = out->bytes / std::max<int64_t>(Count(out), 1);  // element size
+  for (int i = 0; i < axis; ++i) outer *= out->dims->data[i];
+  for (int i = axis + 1; i < r; ++i) inner *= out->dims->data[i];
+  const size_t out_pitch = inner * out->dims->data[axis];
+  size_t off = 0;
+  for (int k = 0; k < n->inputs->size; ++k) {
+    const TfLiteTensor* t = T(c, n->inputs, k);
+    const size_t w = inner * t->dims->data[axis];
+    if (w && outer &&
+        cudaMemcpy2DAsync(out->data.raw + off, out_pitch, t->data.raw, w, w, outer,
+                          cudaMemcpyDefault,
+                          static_cast<cudaStream_t>(lce_b200_get_stream())) != cudaSuccess) {
+      c->ReportError(c, "CONCATENATION: device copy failed");
+      return kTfLiteError;
+    }
+    off += w;
+  }
+  return kTfLiteOk;
+}
+
 }  // namespace
 
 const TfLiteRegistration* FusedPoolDepthwiseRegistration() {
@@ -361,6 +457,11 @@ void RegisterBuiltinOps(OpResolver* r) {
   r->AddBuiltin(40, &mean);
   r->AddBuiltin(25, &softmax);
   r->AddBuiltin(22, &reshape);
+  static TfLiteRegistration pad = {Init, Free, PadPrepare, PadInvoke};
+  static TfLiteRegistration concat = {Init, Free, ConcatPrepare, ConcatInvoke};
+  r->AddBuiltin(34, &pad);   // PAD
+  r->AddBuiltin(60, &pad);   // PADV2
+  r->AddBuiltin(2, &concat);  // CONCATENATION
 }
 
 }  // namespace lce_b200

@@ -13,6 +13,7 @@ struct BuiltinParams {
   int32_t filter_h, filter_w, depth_multiplier;
   int32_t activation;
   int32_t keep_dims;
+  int32_t axis;
   float beta;
   int32_t n_new_shape;
   int32_t new_shape[8];

@@ -139,6 +139,7 @@ bool BuildGraphFromTflite(const uint8_t* data, size_t size, const OpResolver& re
     Vec in = op.vec(1, 4);
     for (uint32_t k = 0; k < in.len; ++k) {
       const int32_t t = in.at<int32_t>(k);
+      if ((bc == 34 || bc == 60) && k >= 1) continue;  // PAD paddings / PADV2 value: read on host
       if (t >= 0 && static_cast<uint32_t>(t) < tensors.len) builtin_const[t] = 1;
     }
   }
@@ -252,6 +253,10 @@ bool BuildGraphFromTflite(const uint8_t* data, size_t size, const OpResolver& re
       case 0:
       case 18:  // ADD / MUL (schema.fbs:939,945)
         bp.activation = o.scalar<int8_t>(0, 0);
+        break;
+      case 2:  // CONCATENATION (schema.fbs:934)
+        bp.axis = o.scalar<int32_t>(0, 0);
+        bp.activation = o.scalar<int8_t>(1, 0);
         break;
       case 40:  // MEAN: ReducerOptions (schema.fbs:1106)
         bp.keep_dims = o.scalar<int8_t>(0, 0);

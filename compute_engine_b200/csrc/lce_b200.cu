@@ -126,48 +126,19 @@ struct GemmCore {
   }
 };
 
-int sm_count() {
-  static int n = 0;
-  if (!n) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
-      n = 148;
-  }
-  return n;
+// Dynamic shared memory one CTA may use so that kCtasPerSm CTAs stay resident on an SM
+// (227 KB per SM, 1 KB reserved per CTA, a little static shared memory).
+size_t cta_smem_budget() {
+  return (227u * 1024u / lce::kCtasPerSm - 1024u - 256u) & ~size_t{127};
 }
 
 template <int V, int OUT>
 int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  // K in one chunk: persistent kernel (weights + epilogue vectors resident, two-stage
-  // gather ring); otherwise one CTA per tile with K staged chunk by chunk.
-  // MEASURED SLOWER than the one-shot kernel on every QuickNet layer (S1 0.193 -> 0.208 ms,
-  // S3 0.151 -> 0.181 ms, profiles/r01_persistent_experiment.txt): the four resident CTAs of an
-  // SM run in lock-step, so the inter-CTA overlap of gather / compute / epilogue phases that
-  // the hardware block scheduler gives the one-shot kernel for free is lost. Kept for
-  // experiments behind LCE_B200_PERSISTENT=1; off by default.
-  static const bool use_persistent = [] {
-    const char* e = getenv("LCE_B200_PERSISTENT");
-    return e && e[0] == '1';
-  }();
-  const size_t psmem = static_cast<size_t>(p.Kv) * (lce::kBN + 2 * lce::kBM) * V * 4;
-  if (use_persistent && p.n_chunks == 1 && psmem <= 80 * 1024) {
-    static bool pattr_set = false;
-    if (!pattr_set) {
-      CUDA_OK(cudaFuncSetAttribute(lce::bconv_persistent_kernel<V, OUT>,
-                                   cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
-      pattr_set = true;
-    }
-    const unsigned ctas = static_cast<unsigned>(sm_count() * lce::kCtasPerSm);
-    dim3 pgrid(std::max(1u, std::min(grid.x, ctas / std::max(1u, grid.y))), grid.y);
-    lce::bconv_persistent_kernel<V, OUT><<<pgrid, lce::kThreads, psmem, s>>>(p);
-    return launch_check("bconv_persistent_kernel");
-  }
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_OK(cudaFuncSetAttribute(lce::bconv_kernel<V, OUT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (lce::kBM + lce::kBN) * lce::kMaxChunkWords * 4));
+                                 static_cast<int>(cta_smem_budget())));
     attr_set = true;
   }
   lce::bconv_kernel<V, OUT><<<grid, lce::kThreads, smem, s>>>(p);
@@ -184,15 +155,23 @@ int launch_conv_v(int out_type, const lce::ConvKParams& p, dim3 grid, size_t sme
   }
   return fail("unsupported output type %d", out_type);
 }
-int launch_conv(const GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
+int launch_conv(const GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
+  p.fd_ohw = lce::make_fastdiv(static_cast<uint32_t>(p.OH) * p.OW);
+  p.fd_ow = lce::make_fastdiv(p.OW);
+  p.fd_cwv = lce::make_fastdiv(p.CwV);
+  p.fd_kw = lce::make_fastdiv(p.KW);
+  p.fd_tpg = lce::make_fastdiv(p.tiles_per_group);
+  p.img_words = static_cast<long long>(p.H) * p.W * p.Cw_total;
   if (p.M <= 0) return 0;  // empty batch: nothing to do
   const long long m_tiles = (p.M + lce::kBM - 1) / lce::kBM;
   if (m_tiles > INT_MAX) return fail("too many output pixels");
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(c.groups * c.tiles_per_group));
+  const size_t smem = c.smem_bytes + (p.res_stage ? lce::kResStageBytes : 0);
+  if (p.img_words >= (1LL << 31)) return fail("input image too large (>= 2^31 packed words)");
   switch (c.V) {
-    case 4: return launch_conv_v<4>(c.out_type, p, grid, c.smem_bytes, s);
-    case 2: return launch_conv_v<2>(c.out_type, p, grid, c.smem_bytes, s);
-    default: return launch_conv_v<1>(c.out_type, p, grid, c.smem_bytes, s);
+    case 4: return launch_conv_v<4>(c.out_type, p, grid, smem, s);
+    case 2: return launch_conv_v<2>(c.out_type, p, grid, smem, s);
+    default: return launch_conv_v<1>(c.out_type, p, grid, smem, s);
   }
 }
 
@@ -525,6 +504,15 @@ static int bconv_run_impl(lce_b200_bconv2d* plan, const int32_t* in_dev, void* o
   else
     p.vec_store = (c.cout % 4 == 0 && c.cout_pg % 4 == 0 && aligned16(out_dev));
   p.bp_fast = (c.groups == 1 || c.cout_pg % 32 == 0);
+  // Stage the shortcut rows through shared memory when every tile is full (so each thread
+  // owns 8 valid, 16-byte aligned channels) and the extra 16 KB keep the CTAs/SM resident.
+  static const bool res_stage_on = [] {
+    const char* e = getenv("LCE_B200_RES_STAGE");
+    return !(e && e[0] == '0');
+  }();
+  p.res_stage = res_stage_on && residual != nullptr && d.out_type == LCE_OUT_FLOAT &&
+                p.vec_store && c.cout_pg % lce::kBN == 0 &&
+                c.smem_bytes + lce::kResStageBytes <= cta_smem_budget();
   if (p.M == 0) return 0;
   // The 4V-byte cp.async gathers need 4V-byte aligned pixels.
   if ((reinterpret_cast<uintptr_t>(in_dev) & (4u * c.V - 1)) != 0)
@@ -656,10 +644,10 @@ int lce_b200_bgemm_run(lce_b200_bgemm* plan, int64_t M, const int32_t* A_dev, vo
   p.in = A_dev; p.wt = c.wt; p.out = out_dev;
   p.mul = c.mul; p.bias = c.bias; p.thr = c.thr; p.tap_popc = nullptr;
   p.M = M;
-  p.H = 1; p.W = static_cast<int>(M);
+  p.H = 1; p.W = 1;  // every row of A is its own 1 x 1 "image": offsets stay 32-bit
   p.Cw_total = plan->Kw; p.Cw_pg = plan->Kw; p.CwV = plan->Kw / c.V;
   p.KH = p.KW = 1; p.sh = p.sw = p.dh = p.dw = 1; p.ph = p.pw = 0;
-  p.OH = 1; p.OW = static_cast<int>(M);
+  p.OH = 1; p.OW = 1;
   p.cout = c.cout; p.cout_pg = c.cout_pg; p.tiles_per_group = c.tiles_per_group;
   p.Kv = c.Kv; p.Kc_v = c.Kc_v; p.n_chunks = c.n_chunks;
   p.clamp_min = c.clamp_min; p.clamp_max = c.clamp_max;

@@ -634,6 +634,29 @@ __global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ 
   for (int c = lane; c < cols; c += 32) y[c] = expf((x[c] - mx) * beta) / sum;
 }
 
+// constant pad of a 4-D tensor of 32-bit elements (float32, or bitpacked int32 words).
+struct Pad4 { int in[4], out[4], before[4]; };
+__global__ void __launch_bounds__(256) pad4d32_kernel(const uint32_t* __restrict__ in,
+                                                      uint32_t* __restrict__ out, Pad4 p,
+                                                      uint32_t fill, long long total) {
+  const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (i >= total) return;
+  long long r = i;
+  const int d3 = static_cast<int>(r % p.out[3]); r /= p.out[3];
+  const int d2 = static_cast<int>(r % p.out[2]); r /= p.out[2];
+  const int d1 = static_cast<int>(r % p.out[1]); r /= p.out[1];
+  const int d0 = static_cast<int>(r);
+  const int s0 = d0 - p.before[0], s1 = d1 - p.before[1], s2 = d2 - p.before[2],
+            s3 = d3 - p.before[3];
+  uint32_t v = fill;
+  if (static_cast<unsigned>(s0) < static_cast<unsigned>(p.in[0]) &&
+      static_cast<unsigned>(s1) < static_cast<unsigned>(p.in[1]) &&
+      static_cast<unsigned>(s2) < static_cast<unsigned>(p.in[2]) &&
+      static_cast<unsigned>(s3) < static_cast<unsigned>(p.in[3]))
+    v = in[((static_cast<long long>(s0) * p.in[1] + s1) * p.in[2] + s2) * p.in[3] + s3];
+  out[i] = v;
+}
+
 int make_geom(const lce_f32_conv_desc* d, ConvGeom* g) {
   if (d->batch < 0 || d->in_h < 1 || d->in_w < 1 || d->in_c < 1 || d->out_c < 1 ||
       d->filter_h < 1 || d->filter_w < 1 || d->stride_h < 1 || d->stride_w < 1 ||
@@ -868,6 +891,25 @@ int lce_b200_f32_softmax(const float* in, float* out, int64_t rows, int cols, fl
   softmax_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
       in, out, rows, cols, beta);
   return launch_check("softmax_kernel");
+}
+
+int lce_b200_pad4d_32(const void* in, void* out, const int32_t* in_dims,
+                      const int32_t* pad_before, const int32_t* pad_after, uint32_t fill_bits,
+                      void* stream) {
+  Pad4 p;
+  long long total = 1;
+  for (int i = 0; i < 4; ++i) {
+    if (in_dims[i] < 0 || pad_before[i] < 0 || pad_after[i] < 0)
+      return fail("pad: negative dimension or padding");
+    p.in[i] = in_dims[i];
+    p.before[i] = pad_before[i];
+    p.out[i] = in_dims[i] + pad_before[i] + pad_after[i];
+    total *= p.out[i];
+  }
+  if (total == 0) return 0;
+  pad4d32_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, as_stream(stream)>>>(
+      static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), p, fill_bits, total);
+  return launch_check("pad4d32_kernel");
 }
 
 }  // extern "C"

@@ -32,12 +32,37 @@ namespace lce {
 constexpr int kBM = LCE_BM;
 constexpr int kBN = 64;
 constexpr int kThreads = 2 * kBM;          // two gather threads per pixel; one warp per 16 pixels
-constexpr int kCtasPerSm = 512 / kThreads;  // 2 CTAs of 256 threads or 4 of 128 (register bound)
+#ifndef LCE_CTAS
+#define LCE_CTAS (512 / (2 * LCE_BM))
+#endif
+constexpr int kCtasPerSm = LCE_CTAS;  // 2 CTAs of 256 threads or 4 of 128 (register bound)
 constexpr int kTM = 4;
 constexpr int kTN = 8;
 // Upper bound on K words staged per chunk so that kCtasPerSm CTAs fit in 227 KB of shared
 // memory: (BM+BN)*Kc*4 B <= 96 KiB (BM 128, 2 CTAs/SM) or 48 KiB (BM 64, 4 CTAs/SM).
-constexpr int kMaxChunkWords = (kBM == 128) ? 128 : 96;
+constexpr int kMaxChunkWords = (kBM == 128) ? 128 : (kCtasPerSm <= 4 ? 96 : 72);
+
+// Division by a launch-constant with one wide multiply and a shift (the index decompositions in
+// the gather and the epilogue otherwise cost ~25 instructions each). Exact for 0 <= n < 2^31:
+// mul = floor(2^(31+L)/d) + 1, L = ceil(log2 d), q = (n * mul) >> (31 + L).
+struct FastDiv {
+  uint32_t mul, shift;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+  FastDiv f;
+  uint32_t L = 0;
+  while ((1ull << L) < d) ++L;
+  f.mul = static_cast<uint32_t>(((1ull << (31 + L)) / (d ? d : 1)) + 1);
+  f.shift = 31 + L;
+  return f;
+}
+__device__ __forceinline__ uint32_t fdiv(uint32_t n, FastDiv d) {
+  return static_cast<uint32_t>((static_cast<unsigned long long>(n) * d.mul) >> d.shift);
+}
+
+// Fused shortcut: each thread parks its own 4 x 8 residual values (8 x 16 B) in shared memory
+// with cp.async at kernel start, so the epilogue never waits on L2 / HBM.
+constexpr int kResStageBytes = kThreads * 8 * 16;
 
 struct ConvKParams {
   const int32_t* in;        // bitpacked NHWC activations
@@ -62,6 +87,9 @@ struct ConvKParams {
   int zp_half;       // channels_in_per_group / 2 (zero-padding correction)
   int vec_store;     // output rows are 16B-aligned for this thread's 8 channels
   int bp_fast;       // bitpacked output: tiles start on a 32-channel boundary
+  int res_stage;     // residual rows are staged through shared memory (kResStageBytes extra)
+  FastDiv fd_ohw, fd_ow, fd_cwv, fd_kw, fd_tpg;  // / (OH*OW), / OW, / CwV, / KW, / tiles_per_group
+  long long img_words;  // H * W * Cw_total (< 2^31, checked by the host)
 };
 
 // --------------------------- PTX helpers ---------------------------------- //
@@ -109,6 +137,21 @@ __device__ __forceinline__ void cp_async_zfill(void* dst_smem, const void* src, 
   asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(smem_u32(dst_smem)),
                "l"(src), "n"(BYTES), "r"(src_bytes)
                : "memory");
+}
+template <int BYTES>
+__device__ __forceinline__ void cp_async_zfill_u32(uint32_t dst_smem, const void* src,
+                                                   int src_bytes) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], %2, %3;" ::"r"(dst_smem), "l"(src),
+               "n"(BYTES), "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_cg16(void* dst_smem, const void* src, int src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(dst_smem)), "l"(src),
+               "r"(src_bytes)
+               : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void cp_async_wait_all() {
   asm volatile("cp.async.wait_all;" ::: "memory");
@@ -194,13 +237,33 @@ __device__ __forceinline__ int round_saturate_i8(float y) {
 // zero-filling 4V-byte cp.async (out-of-bounds taps read as 0 bits = +1, the
 // reference's one-padding: reference.h:106, optimized_bgemm.h:30-31).
 // ------------------------------------------------------------------------- //
-// ---- shared device functions of the one-shot and the persistent kernel ----------------
+// ---- device functions of the implicit-GEMM kernel ----------------
+
+// Decompose output pixel m into (batch image, oy, ox). 32-bit fast division when the pixel
+// count allows it (always, in practice); a 64-bit divide otherwise.
+__device__ __forceinline__ void split_pixel(const ConvKParams& p, long long m, long long* b,
+                                            int* oy, int* ox) {
+  uint32_t r;
+  if (p.M < (1LL << 31)) {
+    const uint32_t bb = fdiv(static_cast<uint32_t>(m), p.fd_ohw);
+    r = static_cast<uint32_t>(m) - bb * static_cast<uint32_t>(p.OH * p.OW);
+    *b = bb;
+  } else {
+    const int ohw = p.OH * p.OW;
+    *b = m / ohw;
+    r = static_cast<uint32_t>(m - *b * ohw);
+  }
+  const uint32_t y = fdiv(r, p.fd_ow);
+  *oy = static_cast<int>(y);
+  *ox = static_cast<int>(r - y * static_cast<uint32_t>(p.OW));
+}
 
 // Gather one K chunk of the im2col rows of tile `m0` into A_buf[kv - kv0][pixel] with
 // zero-filling cp.async. Thread t handles pixel t % BM and every second k-vector.
 template <int V>
 __device__ __forceinline__ void gather_tile(const ConvKParams& p, typename VecT<V>::T* A_buf,
                                             long long m0, int g, int kv0, int kv1, int tid) {
+  using Vec = typename VecT<V>::T;
   const int lp = tid & (kBM - 1);
   const int half = tid / kBM;
   const long long gm = m0 + lp;
@@ -208,33 +271,28 @@ __device__ __forceinline__ void gather_tile(const ConvKParams& p, typename VecT<
   int iy0 = 0, ix0 = 0;
   const int32_t* img = p.in;
   if (pix_valid) {
-    const int ohw = p.OH * p.OW;
-    // 32-bit division when the pixel count allows it (a 64-bit divide is ~100 instructions)
-    const long long b = p.M < (1LL << 31) ? static_cast<long long>(static_cast<unsigned>(gm) /
-                                                                   static_cast<unsigned>(ohw))
-                                          : gm / ohw;
-    const int r = static_cast<int>(gm - b * ohw);
-    const int oy = r / p.OW;
-    const int ox = r - oy * p.OW;
+    long long b;
+    int oy, ox;
+    split_pixel(p, gm, &b, &oy, &ox);
     iy0 = oy * p.sh - p.ph;
     ix0 = ox * p.sw - p.pw;
-    img = p.in + b * p.H * static_cast<long long>(p.W) * p.Cw_total +
-          static_cast<long long>(g) * p.Cw_pg;
+    img = p.in + b * p.img_words + g * p.Cw_pg;
   }
   int kv = kv0 + half;
-  int tap = kv / p.CwV;
+  int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kv), p.fd_cwv));
   int cv = kv - tap * p.CwV;
-  int fy = tap / p.KW;
+  int fy = static_cast<int>(fdiv(static_cast<uint32_t>(tap), p.fd_kw));
   int fx = tap - fy * p.KW;
-  for (; kv < kv1; kv += 2) {
+  uint32_t dst = smem_u32(A_buf + half * kBM + lp);
+  for (; kv < kv1; kv += 2, dst += 2 * kBM * static_cast<uint32_t>(sizeof(Vec))) {
     const int iy = iy0 + fy * p.dh;
     const int ix = ix0 + fx * p.dw;
     const bool inside = pix_valid && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
                         static_cast<unsigned>(ix) < static_cast<unsigned>(p.W);
-    const int32_t* src =
-        inside ? img + (static_cast<long long>(iy) * p.W + ix) * p.Cw_total + cv * V : p.in;
-    cp_async_zfill<V * 4>(&A_buf[static_cast<size_t>(kv - kv0) * kBM + lp], src,
-                          inside ? V * 4 : 0);
+    // offsets inside one image fit 32 bits (img_words < 2^31)
+    const int off = (iy * p.W + ix) * p.Cw_total + cv * V;
+    const int32_t* src = inside ? img + off : p.in;
+    cp_async_zfill_u32<V * 4>(dst, src, inside ? V * 4 : 0);
     cv += 2;
     while (cv >= p.CwV) {
       cv -= p.CwV;
@@ -259,6 +317,30 @@ __device__ __forceinline__ void compute_chunk(const typename VecT<V>::T* A_s,
     // profiles/r01_microbench_pipes.jsonl).
     constexpr int G = 8 / V;  // smem vectors per 8-word group
     int kv = 0;
+#ifdef LCE_HALF_TILE
+    // two pixels at a time: 16 instead of 32 live activation registers (the weight words are
+    // re-read from shared memory for the second half), so more CTAs fit per SM
+    for (; kv + G <= nkv; kv += G) {
+#pragma unroll
+      for (int h = 0; h < kTM / 2; ++h) {
+        uint32_t a[2][8];
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+#pragma unroll
+          for (int gq = 0; gq < G; ++gq)
+            load_words<V>(a_ptr + (kv + gq) * kBM + (h * 2 + i) * 4, &a[i][gq * V]);
+#pragma unroll
+        for (int j = 0; j < kTN; ++j) {
+          uint32_t w[8];
+#pragma unroll
+          for (int gq = 0; gq < G; ++gq) load_words<V>(w_ptr + (kv + gq) * kBN + j * 8, &w[gq * V]);
+#pragma unroll
+          for (int i = 0; i < 2; ++i) acc[h * 2 + i][j] = xor_popc8_acc(a[i], w, acc[h * 2 + i][j]);
+        }
+        asm volatile("" ::: "memory");
+      }
+    }
+#else
     for (; kv + G <= nkv; kv += G) {
       uint32_t a[kTM][8];
 #pragma unroll
@@ -274,6 +356,7 @@ __device__ __forceinline__ void compute_chunk(const typename VecT<V>::T* A_s,
         for (int i = 0; i < kTM; ++i) acc[i][j] = xor_popc8_acc(a[i], w, acc[i][j]);
       }
     }
+#endif
     for (; kv < nkv; ++kv) {  // K tail (< 8 words): plain XOR + POPC
       Vec a[kTM], w[kTN];
 #pragma unroll
@@ -287,6 +370,118 @@ __device__ __forceinline__ void compute_chunk(const typename VecT<V>::T* A_s,
     }
 }
 
+// SAME padding with pad value 0, in integers as the reference kernel does it
+// (reference.h:76-77,100-103): an out-of-bounds tap contributes channels_in_per_group/2
+// instead of popc(0 ^ w). Applied to the accumulators before the output transform.
+__device__ __forceinline__ void zero_pad_correction(const ConvKParams& p, int (&acc)[kTM][kTN],
+                                                    long long m0, int warp, int tm, int c0) {
+  const int taps = p.KH * p.KW;
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    const long long m = m0 + warp * 16 + i * 4 + tm;
+    if (m >= p.M) continue;
+    long long b;
+    int oy, ox;
+    split_pixel(p, m, &b, &oy, &ox);
+    // interior pixels (the vast majority) have no out-of-bounds tap
+    const int iy_lo = oy * p.sh - p.ph, ix_lo = ox * p.sw - p.pw;
+    if (iy_lo >= 0 && ix_lo >= 0 && iy_lo + (p.KH - 1) * p.dh < p.H &&
+        ix_lo + (p.KW - 1) * p.dw < p.W)
+      continue;
+    for (int fy = 0; fy < p.KH; ++fy) {
+      const int iy = iy_lo + fy * p.dh;
+      const bool yin = static_cast<unsigned>(iy) < static_cast<unsigned>(p.H);
+      for (int fx = 0; fx < p.KW; ++fx) {
+        const int ix = ix_lo + fx * p.dw;
+        if (yin && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)) continue;
+        const int t = fy * p.KW + fx;
+#pragma unroll
+        for (int j = 0; j < kTN; ++j)
+          acc[i][j] += p.zp_half - p.tap_popc[static_cast<size_t>(c0 + j) * taps + t];
+      }
+    }
+  }
+}
+
+// Straight-line epilogues for the common case: the tile lies fully inside M and the group's
+// channels, rows are 16-byte aligned. No per-element predicates, row pointers advance by a
+// constant. `res_s`: this thread's staged shortcut values (or nullptr -> global loads).
+__device__ __forceinline__ void epilogue_float_fast(const ConvKParams& p, int (&acc)[kTM][kTN],
+                                                    long long m0, int c_tile, int warp, int tm,
+                                                    int tn, const float* mulp, const float* biasp,
+                                                    const float4* res_s) {
+  const float4 mu0 = reinterpret_cast<const float4*>(mulp)[0];
+  const float4 mu1 = reinterpret_cast<const float4*>(mulp)[1];
+  const float4 bi0 = reinterpret_cast<const float4*>(biasp)[0];
+  const float4 bi1 = reinterpret_cast<const float4*>(biasp)[1];
+  const float mul_r[kTN] = {mu0.x, mu0.y, mu0.z, mu0.w, mu1.x, mu1.y, mu1.z, mu1.w};
+  const float bias_r[kTN] = {bi0.x, bi0.y, bi0.z, bi0.w, bi1.x, bi1.y, bi1.z, bi1.w};
+  const long long mrow = m0 + warp * 16 + tm;
+  const size_t e0 = static_cast<size_t>(mrow) * p.cout + c_tile + tn * 8;
+  const size_t estep = static_cast<size_t>(4) * p.cout;
+  float* o = static_cast<float*>(p.out) + e0;
+  const float* r = p.residual + e0;  // only dereferenced when residual != nullptr
+  int32_t* pk = p.packed_out + static_cast<size_t>(mrow) * p.cw_out + (c_tile >> 5) + (tn >> 2);
+  const bool has_res = p.residual != nullptr;
+  const bool has_pk = p.packed_out != nullptr;
+  const int ract = p.residual_act;
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    float y[kTN];
+#pragma unroll
+    for (int j = 0; j < kTN; ++j)
+      y[j] = transform_float(acc[i][j], p.clamp_min, p.clamp_max, mul_r[j], bias_r[j]);
+    if (has_res) {
+      const float4 r0 = res_s ? res_s[(i * 2) * kThreads] : reinterpret_cast<const float4*>(r)[0];
+      const float4 r1 =
+          res_s ? res_s[(i * 2 + 1) * kThreads] : reinterpret_cast<const float4*>(r)[1];
+      y[0] = __fadd_rn(y[0], r0.x); y[1] = __fadd_rn(y[1], r0.y);
+      y[2] = __fadd_rn(y[2], r0.z); y[3] = __fadd_rn(y[3], r0.w);
+      y[4] = __fadd_rn(y[4], r1.x); y[5] = __fadd_rn(y[5], r1.y);
+      y[6] = __fadd_rn(y[6], r1.z); y[7] = __fadd_rn(y[7], r1.w);
+      if (ract == LCE_ACT_RELU) {
+#pragma unroll
+        for (int j = 0; j < kTN; ++j) y[j] = fmaxf(y[j], 0.0f);
+      } else if (ract == LCE_ACT_RELU6) {
+#pragma unroll
+        for (int j = 0; j < kTN; ++j) y[j] = fminf(fmaxf(y[j], 0.0f), 6.0f);
+      } else if (ract == LCE_ACT_RELU_N1_TO_1) {
+#pragma unroll
+        for (int j = 0; j < kTN; ++j) y[j] = fminf(fmaxf(y[j], -1.0f), 1.0f);
+      }
+    }
+    reinterpret_cast<float4*>(o)[0] = make_float4(y[0], y[1], y[2], y[3]);
+    reinterpret_cast<float4*>(o)[1] = make_float4(y[4], y[5], y[6], y[7]);
+    if (has_pk) {
+      // LceQuantize of the value just written: bit = value < 0 (bitpack.h:159)
+      uint32_t bits = 0;
+#pragma unroll
+      for (int j = 0; j < kTN; ++j) bits |= (y[j] < 0.0f) ? (1u << j) : 0u;
+      uint32_t v = bits << (8 * (tn & 3));
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      v |= __shfl_xor_sync(0xffffffffu, v, 2);
+      if ((tn & 3) == 0) *pk = static_cast<int32_t>(v);
+      pk += static_cast<size_t>(4) * p.cw_out;
+    }
+    o += estep;
+    r += estep;
+  }
+}
+
+__device__ __forceinline__ void epilogue_raw_fast(const ConvKParams& p, int (&acc)[kTM][kTN],
+                                                  long long m0, int c_tile, int warp, int tm,
+                                                  int tn) {
+  int* o = static_cast<int*>(p.out) +
+           static_cast<size_t>(m0 + warp * 16 + tm) * p.cout + c_tile + tn * 8;
+  const size_t estep = static_cast<size_t>(4) * p.cout;
+#pragma unroll
+  for (int i = 0; i < kTM; ++i) {
+    reinterpret_cast<int4*>(o)[0] = make_int4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+    reinterpret_cast<int4*>(o)[1] = make_int4(acc[i][4], acc[i][5], acc[i][6], acc[i][7]);
+    o += estep;
+  }
+}
+
 // Position j*8+tn of the weight tile holds channel tn*8+j, so each thread owns 8 CONSECUTIVE
 // output channels and stores them with 128-bit writes. mulp / biasp / thrp point at this
 // thread's first channel (global memory, or the persistent kernel's shared-memory copy).
@@ -294,12 +489,23 @@ template <int OUT>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, int (&acc)[kTM][kTN],
                                               long long m0, int g, int tg, int warp, int tm,
                                               int tn, const float* mulp, const float* biasp,
-                                              const int32_t* thrp) {
+                                              const int32_t* thrp,
+                                              const float4* res_s = nullptr) {
   const int c_tile = g * p.cout_pg + tg * kBN;
   const int valid = min(kBN, p.cout_pg - tg * kBN);
   const int cofs = tn * 8;
   const int c0 = c_tile + cofs;
-  const int taps = p.KH * p.KW;
+  if (p.tap_popc != nullptr) zero_pad_correction(p, acc, m0, warp, tm, c0);
+  if (cofs + kTN <= valid && p.vec_store && m0 + kBM <= p.M) {
+    if (OUT == LCE_OUT_FLOAT) {
+      epilogue_float_fast(p, acc, m0, c_tile, warp, tm, tn, mulp, biasp, res_s);
+      return;
+    }
+    if (OUT == LCE_OUT_RAW_ACC) {
+      epilogue_raw_fast(p, acc, m0, c_tile, warp, tm, tn);
+      return;
+    }
+  }
   float mul_r[kTN], bias_r[kTN];
   int thr_r[kTN];
   if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_INT8) {
@@ -318,29 +524,6 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, int (&acc)[k
   for (int i = 0; i < kTM; ++i) {
     const long long m = m0 + warp * 16 + i * 4 + tm;
     const bool row_ok = m < p.M;
-
-    if (p.tap_popc != nullptr && row_ok) {
-      // SAME padding with pad value 0, in integers as the reference kernel does
-      // it (reference.h:76-77,100-103): an out-of-bounds tap contributes
-      // channels_in_per_group/2 instead of popc(0 ^ w).
-      const int ohw = p.OH * p.OW;
-      const long long b = m / ohw;
-      const int r = static_cast<int>(m - b * ohw);
-      const int oy = r / p.OW;
-      const int ox = r - oy * p.OW;
-      for (int fy = 0; fy < p.KH; ++fy) {
-        const int iy = oy * p.sh - p.ph + fy * p.dh;
-        const bool yin = static_cast<unsigned>(iy) < static_cast<unsigned>(p.H);
-        for (int fx = 0; fx < p.KW; ++fx) {
-          const int ix = ox * p.sw - p.pw + fx * p.dw;
-          if (yin && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)) continue;
-          const int t = fy * p.KW + fx;
-#pragma unroll
-          for (int j = 0; j < kTN; ++j)
-            acc[i][j] += p.zp_half - p.tap_popc[static_cast<size_t>(c0 + j) * taps + t];
-        }
-      }
-    }
 
     if (OUT == LCE_OUT_RAW_ACC) {
       if (!row_ok) continue;
@@ -361,9 +544,10 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, int (&acc)[k
       float* o = static_cast<float*>(p.out) + m * p.cout + c0;
       if (p.residual != nullptr && row_ok) {
         const float* r = p.residual + m * p.cout + c0;
-        if (full && p.vec_store) {
-          const float4 r0 = reinterpret_cast<const float4*>(r)[0];
-          const float4 r1 = reinterpret_cast<const float4*>(r)[1];
+        if (res_s != nullptr || (full && p.vec_store)) {
+          const float4 r0 = res_s ? res_s[(i * 2) * kThreads] : reinterpret_cast<const float4*>(r)[0];
+          const float4 r1 =
+              res_s ? res_s[(i * 2 + 1) * kThreads] : reinterpret_cast<const float4*>(r)[1];
           y[0] = __fadd_rn(y[0], r0.x); y[1] = __fadd_rn(y[1], r0.y);
           y[2] = __fadd_rn(y[2], r0.z); y[3] = __fadd_rn(y[3], r0.w);
           y[4] = __fadd_rn(y[4], r1.x); y[5] = __fadd_rn(y[5], r1.y);
@@ -456,7 +640,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, int (&acc)[k
 }
 
 // ------------------------------------------------------------------------- //
-// One-shot kernel: one CTA = one 64 x 64 tile, K staged chunk by chunk (any K).
+// One CTA = one 64 x 64 tile, K staged chunk by chunk (any K). (A persistent, double-buffered
+// variant was measured slower on every layer: profiles/r01_persistent_experiment.txt.)
 // ------------------------------------------------------------------------- //
 template <int V, int OUT>
 __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvKParams p) {
@@ -470,7 +655,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
   const int warp = tid >> 5, lane = tid & 31;
   const int tn = lane & 7, tm = lane >> 3;
   const int nt = blockIdx.y;
-  const int g = nt / p.tiles_per_group;
+  const int g = static_cast<int>(fdiv(static_cast<uint32_t>(nt), p.fd_tpg));
   const int tg = nt - g * p.tiles_per_group;
   const long long m0 = static_cast<long long>(blockIdx.x) * kBM;
 
@@ -488,7 +673,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
 
   // Fused shortcut: start pulling this thread's residual values towards L2 now, so the
   // DRAM latency of the epilogue's loads is covered by the gather + inner product.
-  if (OUT == LCE_OUT_FLOAT && p.residual != nullptr) {
+  float4* R_s = nullptr;
+  if (OUT == LCE_OUT_FLOAT && p.res_stage)
+    R_s = reinterpret_cast<float4*>(W_s + static_cast<size_t>(p.Kc_v) * kBN) + tid;
+  if (OUT == LCE_OUT_FLOAT && p.residual != nullptr && !p.res_stage) {
 #pragma unroll
     for (int i = 0; i < kTM; ++i) {
       const long long m = m0 + warp * 16 + i * 4 + tm;
@@ -508,7 +696,23 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
       bulk_g2s(W_s, p.wt + (static_cast<size_t>(nt) * p.Kv + kv0) * kBN * V, bytes, &wbar);
     }
     gather_tile<V>(p, A_s, m0, g, kv0, kv1, tid);
-    cp_async_wait_all();
+    if (OUT == LCE_OUT_FLOAT && p.res_stage && ch == 0) {
+      // second cp.async group: the residual rows; only the gather group is waited for here
+      cp_async_commit();
+#pragma unroll
+      for (int i = 0; i < kTM; ++i) {
+        const long long m = m0 + warp * 16 + i * 4 + tm;
+        const bool ok = m < p.M;
+        const float* r = ok ? p.residual + m * p.cout + g * p.cout_pg + tg * kBN + tn * 8
+                            : p.residual;
+        cp_async_cg16(R_s + (i * 2) * kThreads, r, ok ? 16 : 0);
+        cp_async_cg16(R_s + (i * 2 + 1) * kThreads, r + 4, ok ? 16 : 0);
+      }
+      cp_async_commit();
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      cp_async_wait_all();
+    }
     mbar_wait(&wbar, phase);
     phase ^= 1u;
     __syncthreads();
@@ -516,79 +720,8 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
     __syncthreads();
   }
   const int c0 = g * p.cout_pg + tg * kBN + tn * 8;
-  epilogue_tile<OUT>(p, acc, m0, g, tg, warp, tm, tn, p.mul + c0, p.bias + c0, p.thr + c0);
-}
-
-// ------------------------------------------------------------------------- //
-// Persistent kernel (K fits one chunk): each CTA keeps its weight tile and epilogue
-// vectors in shared memory and walks over M tiles with a two-stage ring -- the patch
-// gather of tile t+1 (cp.async) is in flight while tile t is multiplied and stored,
-// so neither the gather latency nor the per-CTA set-up is paid per tile.
-// ------------------------------------------------------------------------- //
-template <int V, int OUT>
-__global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_persistent_kernel(const ConvKParams p) {
-  using Vec = typename VecT<V>::T;
-  extern __shared__ __align__(128) unsigned char smem_raw[];
-  Vec* W_s = reinterpret_cast<Vec*>(smem_raw);                       // [Kv][BN]
-  Vec* A_s0 = W_s + static_cast<size_t>(p.Kv) * kBN;                 // [2][Kv][BM]
-  Vec* A_s1 = A_s0 + static_cast<size_t>(p.Kv) * kBM;
-  __shared__ __align__(16) float ep_mul[kBN];
-  __shared__ __align__(16) float ep_bias[kBN];
-  __shared__ __align__(16) int32_t ep_thr[kBN];
-  __shared__ __align__(8) uint64_t wbar;
-
-  const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
-  const int tn = lane & 7, tm = lane >> 3;
-  const int nt = blockIdx.y;
-  const int g = nt / p.tiles_per_group;
-  const int tg = nt - g * p.tiles_per_group;
-  const long long m_tiles = (p.M + kBM - 1) / kBM;
-
-  if (tid == 0) {
-    mbar_init(&wbar, 1);
-    fence_barrier_init();
-    const uint32_t bytes = static_cast<uint32_t>(p.Kv) * kBN * V * 4u;
-    mbar_arrive_expect_tx(&wbar, bytes);
-    bulk_g2s(W_s, p.wt + static_cast<size_t>(nt) * p.Kv * kBN * V, bytes, &wbar);
-  }
-  if (tid < kBN) {
-    const int c = g * p.cout_pg + tg * kBN + tid;
-    if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_INT8) {
-      ep_mul[tid] = p.mul[c];
-      ep_bias[tid] = p.bias[c];
-    } else if (OUT == LCE_OUT_BITPACKED) {
-      ep_thr[tid] = p.thr[c];
-    }
-  }
-  long long t = blockIdx.x;
-  if (t < m_tiles) gather_tile<V>(p, A_s0, t * kBM, g, 0, p.Kv, tid);
-  asm volatile("cp.async.commit_group;" ::: "memory");
-  __syncthreads();          // mbarrier init + epilogue vectors visible
-  mbar_wait(&wbar, 0);      // weights have landed
-
-  int buf = 0;
-  for (; t < m_tiles; t += gridDim.x, buf ^= 1) {
-    Vec* A_cur = buf ? A_s1 : A_s0;
-    Vec* A_nxt = buf ? A_s0 : A_s1;
-    const long long tn_ = t + gridDim.x;
-    // the other buffer was last read by compute(t - 1); the barrier after that compute
-    // (below) makes it safe to refill now
-    if (tn_ < m_tiles) gather_tile<V>(p, A_nxt, tn_ * kBM, g, 0, p.Kv, tid);
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_group 1;" ::: "memory");   // this tile's gather is complete
-    __syncthreads();
-    int acc[kTM][kTN];
-#pragma unroll
-    for (int i = 0; i < kTM; ++i)
-#pragma unroll
-      for (int j = 0; j < kTN; ++j) acc[i][j] = 0;
-    compute_chunk<V>(A_cur, W_s, p.Kv, warp, tm, tn, acc);
-    __syncthreads();          // everyone is done reading A_cur
-    epilogue_tile<OUT>(p, acc, t * kBM, g, tg, warp, tm, tn, ep_mul + tn * 8, ep_bias + tn * 8,
-                       ep_thr + tn * 8);
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (OUT == LCE_OUT_FLOAT && p.res_stage) cp_async_wait_all();  // own slots only: no barrier
+  epilogue_tile<OUT>(p, acc, m0, g, tg, warp, tm, tn, p.mul + c0, p.bias + c0, p.thr + c0, R_s);
 }
 
 // Re-lay the OHWI-packed filter [cout][taps][Cw_pg] into the kernel's tiles:

@@ -110,10 +110,11 @@ TENSOR_TYPE = {np.dtype(np.float32): 0, np.dtype(np.int32): 2, np.dtype(np.uint8
                np.dtype(np.int64): 4, np.dtype(np.bool_): 6, np.dtype(np.int8): 9}
 OP = {"ADD": 0, "AVERAGE_POOL_2D": 1, "CONV_2D": 3, "DEPTHWISE_CONV_2D": 4,
       "FULLY_CONNECTED": 9, "MAX_POOL_2D": 17, "MUL": 18, "RELU": 19, "RESHAPE": 22,
-      "SOFTMAX": 25, "MEAN": 40, "CUSTOM": 32}
+      "SOFTMAX": 25, "MEAN": 40, "CUSTOM": 32, "CONCATENATION": 2, "PAD": 34, "PADV2": 60}
 # BuiltinOptions union tags (schema_generated.h:1652-1694)
 OPT_TAG = {"CONV_2D": 1, "DEPTHWISE_CONV_2D": 2, "AVERAGE_POOL_2D": 5, "MAX_POOL_2D": 5,
-           "FULLY_CONNECTED": 8, "SOFTMAX": 9, "ADD": 11, "MUL": 21, "RESHAPE": 17, "MEAN": 27}
+           "FULLY_CONNECTED": 8, "SOFTMAX": 9, "ADD": 11, "MUL": 21, "RESHAPE": 17, "MEAN": 27,
+           "CONCATENATION": 10, "PAD": 22, "PADV2": 43}
 PADDING = {"SAME": 0, "VALID": 1}
 ACT = {"NONE": 0, "RELU": 1, "RELU_N1_TO_1": 2, "RELU6": 3}
 
@@ -166,6 +167,10 @@ class TFLiteModel:
             return fb.table({0: ("o", fb.scalar_vector("i", o["new_shape"]))})
         if kind == "MEAN":
             return fb.table({0: ("b", 1 if o.get("keep_dims", False) else 0)})
+        if kind == "CONCATENATION":
+            return fb.table({0: ("i", int(o.get("axis", 0))), 1: ("b", act)})
+        if kind in ("PAD", "PADV2"):
+            return fb.table({})
         return None
 
     def serialize(self) -> bytes:

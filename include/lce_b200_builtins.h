@@ -70,6 +70,12 @@ int lce_b200_f32_mean_hw(const float* in_dev, float* out_dev, int batch, int h, 
 int lce_b200_f32_softmax(const float* in_dev, float* out_dev, int64_t rows, int cols, float beta,
                          void* stream);
 
+/* PAD / PADV2 (TF/lite/kernels/internal/reference/pad.h) of a 4-D tensor of 32-bit elements
+ * (float32 or bitpacked int32 words): out dims = in + before + after, border = fill_bits. */
+int lce_b200_pad4d_32(const void* in_dev, void* out_dev, const int32_t* in_dims4,
+                      const int32_t* pad_before4, const int32_t* pad_after4, uint32_t fill_bits,
+                      void* stream);
+
 #ifdef __cplusplus
 }
 #endif

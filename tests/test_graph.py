@@ -17,6 +17,7 @@ import lce_testlib as L
 import tflite_ref as R
 from compute_engine_b200 import host as H
 from compute_engine_b200 import zoo
+from compute_engine_b200 import tflite_writer as W
 
 TF_TESTDATA = "/root/reference/third_party/tensorflow/tensorflow/lite/testdata"
 
@@ -105,8 +106,9 @@ def test_readers_on_tflite_own_fixtures():
         g.close()
     blob = open(os.path.join(TF_TESTDATA, "conv_huge_im2col.bin"), "rb").read()
     assert [o["code"] for o in R.parse(blob)["ops"]] == [2, 3, 0]     # CONCATENATION, CONV_2D, ADD
-    with pytest.raises(H.HostError, match="builtin operator 2 is not supported"):
-        H.HostGraph.from_tflite(blob, device_arena=False)
+    g = H.HostGraph.from_tflite(blob, device_arena=False)
+    assert g.num_nodes() == 3
+    g.close()
     blob = open(os.path.join(TF_TESTDATA, "custom_sinh.bin"), "rb").read()
     assert R.parse(blob)["ops"][0]["custom"] == "Sinh"
     with pytest.raises(H.HostError, match="unresolved custom op: Sinh"):
@@ -227,3 +229,56 @@ def test_gpu_fused_graph_is_bit_identical_to_unfused(family):
         outs.append(g.read(g.outputs()[0]))
         g.close()
     assert np.array_equal(outs[0].view(np.uint8), outs[1].view(np.uint8))
+
+
+# ---- PAD / PADV2 / CONCATENATION: the glue the converter leaves around LceBconv2d ---- #
+def _pad_concat_model(batch=2, hw=9, cin=64, cout=32, seed=5):
+    """float x -> LceQuantize -> PADV2(bitpacked words, border word -1 = thirty-two -1 values)
+    -> LceBconv2d VALID -> float PAD (channels) -> CONCATENATION(axis 3) with x."""
+    rng = np.random.default_rng(seed)
+    m = W.TFLiteModel()
+    x = m.add_tensor("x", (batch, hw, hw, cin))
+    xq = m.add_tensor("xq", (batch, hw, hw, cin // 32), np.int32)
+    pads = m.add_tensor("pads", None, np.int32, data=np.array([[0, 0], [1, 1], [1, 1], [0, 0]]))
+    fillv = m.add_tensor("fill", None, np.int32, data=np.array([-1], np.int32).reshape(()))
+    xp = m.add_tensor("xp", (batch, hw + 2, hw + 2, cin // 32), np.int32)
+    filt = rng.integers(-2**31, 2**31 - 1, size=(cout, 3, 3, cin // 32), dtype=np.int64).astype(np.int32)
+    f = m.add_tensor("filter", None, np.int32, data=filt)
+    mul = m.add_tensor("mul", None, np.float32, data=rng.uniform(0.01, 1.5, cout))
+    bias = m.add_tensor("bias", None, np.float32, data=rng.uniform(0.01, 1.5, cout))
+    y = m.add_tensor("y", (batch, hw, hw, cout))
+    m.add_op("LceQuantize", [x], [xq], custom_options=b"")
+    m.add_op("PADV2", [xq, pads, fillv], [xp])
+    m.add_op("LceBconv2d", [xp, f, mul, bias, -1], [y],
+             custom_options=H.bconv2d_options(cin, (1, 1), (1, 1), 1, 1, 0))
+    pads2 = m.add_tensor("pads2", None, np.int32,
+                         data=np.array([[0, 0], [0, 0], [0, 0], [3, 5]]))
+    yp = m.add_tensor("yp", (batch, hw, hw, cout + 8))
+    m.add_op("PAD", [y, pads2], [yp])
+    z = m.add_tensor("z", (batch, hw, hw, cin + cout + 8))
+    m.add_op("CONCATENATION", [x, yp], [z], axis=3)
+    m.inputs, m.outputs = [x], [z]
+    return m.serialize()
+
+
+def test_pad_concat_graph_builds_and_infers_shapes():
+    blob = _pad_concat_model()
+    g = H.HostGraph.from_tflite(blob, device_arena=False)
+    g.allocate_tensors()
+    assert g.shape(g.outputs()[0]) == (2, 9, 9, 64 + 32 + 8)
+    g.close()
+
+
+@pytest.mark.gpu
+def test_gpu_pad_concat_graph_matches_reference():
+    blob = _pad_concat_model()
+    m = R.parse(blob)
+    x = np.random.default_rng(11).standard_normal((2, 9, 9, 64)).astype(np.float32)
+    want, _ = R.run(m, [x])
+    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    g.allocate_tensors()
+    g.write(g.inputs()[0], x)
+    g.invoke()
+    got = g.read(g.outputs()[0])
+    g.close()
+    assert got.shape == want[0].shape and np.array_equal(got, want[0])

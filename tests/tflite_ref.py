@@ -255,6 +255,12 @@ def run(model, inputs, threads=8, lce_impl="oracle", bconv_kind=0):
         elif code == 22:
             shape = o.vector(0, "i") or [int(v) for v in ins[1]]
             out = ins[0].reshape(shape)
+        elif code in (34, 60):       # PAD / PADV2
+            pads = np.asarray(ins[1]).reshape(-1, 2)
+            fill = ins[2].reshape(()) if len(ins) > 2 and ins[2] is not None else 0
+            out = np.pad(ins[0], [(int(a), int(b)) for a, b in pads], constant_values=fill)
+        elif code == 2:              # CONCATENATION
+            out = np.concatenate(ins, axis=o.scalar(0, "i"))
         else:
             raise NotImplementedError(f"op {code} {custom}")
         vals[op["outputs"][0]] = out

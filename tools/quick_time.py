@@ -54,6 +54,20 @@ def main():
                               "word_ops_per_s_T": round(macs / 32 / med / 1e9, 3),
                               "alg_GBps": round(bytes_alg / med / 1e6, 1),
                               "img_per_s": round(B / med * 1e3, 1)}))
+        import ctypes as C
+        res = torch.randn((B, hw, hw, c), device="cuda", generator=g)
+        pk = torch.empty((B, hw, hw, cw), device="cuda", dtype=torch.int32)
+        st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def fused():
+            rc = capi.lib().lce_b200_bconv2d_run_fused(
+                plan._h, C.c_void_p(xp.data_ptr()), C.c_void_p(res.data_ptr()), 0,
+                C.c_void_p(out.data_ptr()), C.c_void_p(pk.data_ptr()), st)
+            assert rc == 0
+        med, best = time_fn(fused)
+        print(json.dumps({"kernel": f"bconv {hw}x{hw}x{c} fused(+ADD+LceQuantize)", "batch": B,
+                          "ms": round(med, 4), "ms_best": round(best, 4),
+                          "word_ops_per_s_T": round(macs / 32 / med / 1e9, 3)}))
         med, best = time_fn(lambda: capi.quantize(xf, out=xp))
         print(json.dumps({"kernel": f"bsign_pack {hw}x{hw}x{c}", "ms": round(med, 4),
                           "alg_GBps": round((xf.numel() * 4 + xp.numel() * 4) / med / 1e6, 1)}))
