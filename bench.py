@@ -165,10 +165,10 @@ def make_stage_inputs(batch, seed):
 
 def ncu_traffic_per_launch():
     """Mean dram__bytes_read + dram__bytes_write per lce::bconv_kernel launch from the committed
-    `ncu --set full` capture of this same command (profiles/r01_ncu_bconv_fused_final_summary.csv:
+    `ncu --set full` capture of this same command (profiles/r01_ncu_bconv_v8_summary.csv:
     the 16 LceBconv2d launches of one QuickNet step), or None."""
     import csv
-    path = os.path.join(REPO, "profiles", "r01_ncu_bconv_fused_final_summary.csv")
+    path = os.path.join(REPO, "profiles", "r01_ncu_bconv_v8_summary.csv")
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -606,7 +606,7 @@ def main_b200(args):
                          "frac": achieved / hbm_peak, "peak_source": peak_src,
                          "traffic": ncu_traffic_per_launch() if args.workload == "quicknet" else None,
                          "traffic_unit": "bytes per launch (mean of the 16 launches of one step, "
-                                         "ncu --set full, profiles/r01_ncu_bconv_fused_final_summary.csv)",
+                                         "ncu --set full, profiles/r01_ncu_bconv_v8_summary.csv)",
                          "alg_bytes_per_launch": r["conv_bytes"] / max(r["n_conv"] // K, 1),
                          "launches_timed": r["n_conv"],
                          "avg_launch_ms": r["conv_s_per_step"] * 1e3 * K / max(r["n_conv"], 1),
