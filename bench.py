@@ -163,12 +163,12 @@ def make_stage_inputs(batch, seed):
     return [rng.standard_normal((batch, hw, hw, c), dtype=np.float32) for (hw, c) in STAGES]
 
 
-def ncu_traffic_per_launch():
+def ncu_traffic_per_launch(fname="r01_ncu_bconv_v8_summary.csv"):
     """Mean dram__bytes_read + dram__bytes_write per lce::bconv_kernel launch from the committed
     `ncu --set full` capture of this same command (profiles/r01_ncu_bconv_v8_summary.csv:
     the 16 LceBconv2d launches of one QuickNet step), or None."""
     import csv
-    path = os.path.join(REPO, "profiles", "r01_ncu_bconv_v8_summary.csv")
+    path = os.path.join(REPO, "profiles", fname)
     try:
         rows = list(csv.reader(open(path)))
         hdr, units = rows[0], rows[1]
@@ -434,7 +434,40 @@ def graph_workload(args, D):
         conv_words += bconv_word_ops(g.shape(outs[0]), g.shape(ins[1]))
         n_conv += 1
     K = args.steps
-    return {"total_ms": total_ms, "e2e_ms": e2e_ms, "clocks": clocks,
+    imma_default = os.environ.get("LCE_B200_BCONV_IMMA", "1") != "0"
+    xor = None
+    if imma_default and D.world == 1 and not os.environ.get("LCE_BENCH_NO_XOR_PASS"):
+        # same graph with every LceBconv2d plan on the XOR + POPC kernel (north_star's inner
+        # product), timed the same way: CUDA-graph replay for the value, eager pass for the kernel
+        os.environ["LCE_B200_BCONV_IMMA"] = "0"
+        try:
+            g2 = H.HostGraph.from_tflite(model_bytes, device_arena=True)
+            if not os.environ.get("LCE_NO_FUSION"):
+                g2.fuse_all()
+            g2.resize_input(g2.inputs()[0], (B, 224, 224, 3))
+            g2.allocate_tensors()
+            gs2 = torch.cuda.ExternalStream(g2.stream())
+            g2.write_ptr(g2.inputs()[0], host_in.data_ptr(), in_bytes)
+            g2.synchronize()
+            g2.enable_cuda_graph(True)
+            for _ in range(max(args.warmup, 3) + 1):
+                g2.invoke()
+            g2.synchronize()
+            x_ms, _, _ = D.timed(g2.invoke, args.steps, g2.synchronize, gs2)
+            g2.enable_cuda_graph(False)
+            g2.enable_profiling(True)
+            g2.invoke(); g2.synchronize(); g2.reset_profile()
+            x_prof, _, _ = D.timed(g2.invoke, args.steps, g2.synchronize, gs2)
+            x_node = g2.node_times_ms()
+            x_conv = sum(x_node[i] for i in range(g2.num_nodes())
+                         if g2.node_name(i).startswith("LceBconv2d"))
+            xor = {"total_ms": x_ms, "conv_s_per_step": x_conv * 1e-3 / K,
+                   "conv_share": x_conv / x_prof if x_prof else None}
+            g2.close()
+        finally:
+            os.environ.pop("LCE_B200_BCONV_IMMA", None)
+    return {"total_ms": total_ms, "e2e_ms": e2e_ms, "clocks": clocks, "xor": xor,
+            "imma": imma_default,
             "launches": per_step_launches * K, "conv_s_per_step": conv_ms * 1e-3 / K,
             "conv_bytes": conv_bytes, "conv_words": conv_words, "n_conv": n_conv * K,
             "conv_share": conv_ms / prof_ms if prof_ms else None,
@@ -515,6 +548,7 @@ def stack_workload(args, D):
             "conv_words": conv_words, "n_conv": len(ev_pairs), "conv_share": conv_ms / total_ms,
             "in_bytes": sum(x.numel() * 4 for x in host_in),
             "out_bytes": sum(x.numel() * 4 for x in host_out),
+            "imma": os.environ.get("LCE_B200_BCONV_IMMA", "1") != "0", "xor": None,
             "timing_note": "CUDA events around every LceBconv2d launch inside the timed region"}
 
 
@@ -573,7 +607,9 @@ def main_b200(args):
             emit({"metric": METRIC["bgemm_sweep"], "value": best["binary_TOPS"],
                               "unit": "binary TOPS", "n_gpus": D.world, "steps": 7, "warmup": 3,
                               "ms_per_step": best["ms"], "higher_is_better": True,
-                              "scaling": "strong", "vs_baseline": None, "dtype": "u32 xor-popcount",
+                              "scaling": "strong", "vs_baseline": None,
+                              "dtype": "u8 x s8 -> s32 on the int8 tensor pipe (== xor-popcount, bit-exact)"
+                              if os.environ.get("LCE_B200_BCONV_IMMA", "1") != "0" else "u32 xor-popcount",
                               "data": "synthetic",
                               "config": {"workload": "bgemm_sweep", "best_point": best,
                                          "points": len(rows),
@@ -592,7 +628,9 @@ def main_b200(args):
             "unit": "images/s", "n_gpus": D.world, "steps": K, "warmup": max(args.warmup, 3),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None,
-            "dtype": "u32 xor-popcount (binary convs) + f32 (builtins, epilogue)",
+            "dtype": ("u8 x s8 -> s32 (binary convs on the int8 tensor pipe, bit-exact with "
+                      "xor-popcount) + f32 (builtins, epilogue)") if r.get("imma") else
+                     "u32 xor-popcount (binary convs) + f32 (builtins, epilogue)",
             "data": "synthetic",
             "config": {"workload": args.workload, "batch_per_gpu": B, "global_batch": B * D.world,
                        "model": f"{args.workload}: synthesised .tflite (random weights, seed 0)",
@@ -601,22 +639,61 @@ def main_b200(args):
                        "l2": "activations per step exceed the 126 MB L2 (largest tensor 205 MB)"},
             "clocks": r["clocks"],
             "gpu_launches": launches,
-            "roofline": {"kernel": "lce::bconv_kernel (LceBconv2d)", "bound": "hbm",
-                         "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "peak_source": peak_src,
-                         "traffic": ncu_traffic_per_launch() if args.workload == "quicknet" else None,
-                         "traffic_unit": "bytes per launch (mean of the 16 launches of one step, "
-                                         "ncu --set full, profiles/r01_ncu_bconv_v8_summary.csv)",
-                         "alg_bytes_per_launch": r["conv_bytes"] / max(r["n_conv"] // K, 1),
-                         "launches_timed": r["n_conv"],
-                         "avg_launch_ms": r["conv_s_per_step"] * 1e3 * K / max(r["n_conv"], 1),
-                         "share_of_step": r["conv_share"], "timing": r["timing_note"],
-                         "int_pipe": {"achieved_word_ops_per_s": r["conv_words"] / r["conv_s_per_step"],
-                                      "naive_popc_peak_per_s": popc_peak,
-                                      "frac": r["conv_words"] / r["conv_s_per_step"] / popc_peak,
-                                      "note": "XOR+POPC is POPC-pipe bound (16/clk/SM measured); "
-                                              ">1.0 = gain of the carry-save adder tree"}},
         }
+        n_launch = max(r["n_conv"] // K, 1)
+
+        def xor_roofline(conv_s, share, traffic):
+            ach = r["conv_bytes"] / conv_s / 1e9
+            return {"kernel": "lce::bconv_kernel (LceBconv2d, XOR + POPC carry-save tree)",
+                    "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "peak_source": peak_src,
+                    "traffic": traffic,
+                    "traffic_unit": "bytes per launch (mean of the 16 launches of one step, "
+                                    "ncu --set full, profiles/r01_ncu_bconv_v8_summary.csv)",
+                    "alg_bytes_per_launch": r["conv_bytes"] / n_launch,
+                    "launches_timed": r["n_conv"],
+                    "avg_launch_ms": conv_s * 1e3 / n_launch,
+                    "share_of_step": share, "timing": r["timing_note"],
+                    "int_pipe": {"achieved_word_ops_per_s": r["conv_words"] / conv_s,
+                                 "naive_popc_peak_per_s": popc_peak,
+                                 "frac": r["conv_words"] / conv_s / popc_peak,
+                                 "note": "XOR+POPC is POPC-pipe bound (16/clk/SM measured); "
+                                         ">1.0 = gain of the carry-save adder tree"}}
+
+        traffic = ncu_traffic_per_launch() if args.workload == "quicknet" else None
+        if r.get("imma"):
+            # dominant kernel = the int8 tensor-pipe variant of the same inner product
+            imma_peak = 148 * 2046.5 * sm_max * 1e6 * 2 / 1e12   # TOP/s, profiles/r01_microbench_mma.jsonl
+            tops = 2 * 32 * r["conv_words"] / r["conv_s_per_step"] / 1e12
+            line["roofline"] = {
+                "kernel": "lce::bconv_imma_kernel (LceBconv2d, u8 x s8 mma.sync m16n8k32 on bitpacked "
+                          "operands, bit-exact)",
+                "bound": "tensor", "achieved": tops, "peak": imma_peak, "unit": "TOP/s (int8)",
+                "frac": tops / imma_peak,
+                "peak_source": "measured here: legacy int8 mma.sync 2046.5 MAC/clk/SM x 148 SMs x "
+                               "SM clock (tools/microbench_mma.cu, profiles/r01_microbench_mma.jsonl); "
+                               "MEASURED_PEAKS.json's bf16 figure is the tcgen05 path and is not a bound "
+                               "for mma.sync int8",
+                "traffic": ncu_traffic_per_launch("r01_ncu_bconv_imma_summary.csv")
+                if args.workload == "quicknet" else None,
+                "traffic_unit": "bytes per launch (ncu --set full, "
+                                "profiles/r01_ncu_bconv_imma_summary.csv)",
+                "alg_bytes_per_launch": r["conv_bytes"] / n_launch,
+                "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": achieved / hbm_peak},
+                "launches_timed": r["n_conv"],
+                "avg_launch_ms": r["conv_s_per_step"] * 1e3 / n_launch,
+                "share_of_step": r["conv_share"], "timing": r["timing_note"]}
+            if r.get("xor"):
+                x = r["xor"]
+                line["xor_popc_path"] = {
+                    "note": "same graph, same run, LCE_B200_BCONV_IMMA=0: every LceBconv2d on the "
+                            "XOR + POPC kernel north_star describes",
+                    "value": B * D.world / (x["total_ms"] / K * 1e-3), "unit": "images/s",
+                    "ms_per_step": x["total_ms"] / K,
+                    "roofline": xor_roofline(x["conv_s_per_step"], x["conv_share"], traffic)}
+        else:
+            line["roofline"] = xor_roofline(r["conv_s_per_step"], r["conv_share"], traffic)
         if r.get("e2e_ms") is not None:
             line["e2e"] = {"value": B * D.world / (r["e2e_ms"] / K * 1e-3), "unit": "images/s",
                            "h2d_bytes_per_step": r["in_bytes"],

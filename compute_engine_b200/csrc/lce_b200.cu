@@ -18,6 +18,7 @@
 
 #include "lce_b200.h"
 #include "lce_b200_kernels.cuh"
+#include "lce_b200_imma.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -119,10 +120,16 @@ struct GemmCore {
   int32_t* thr = nullptr;
   int32_t* tap_popc = nullptr;  // zero-padding correction table
   size_t smem_bytes = 0;
+  // experimental int8-tensor-pipe inner product (lce_b200_imma.cuh), LCE_B200_BCONV_IMMA=1
+  int32_t* wt_nat = nullptr;    // weights expanded to int8 mma B fragments (8x the packed bytes)
+  int32_t* wpop = nullptr;      // popcount of each channel's filter row (padded by BN)
+  int imma_Kc_v = 0, imma_chunks = 1;
+  size_t imma_smem = 0;
 
   void release() {
     cudaFree(wt); cudaFree(mul); cudaFree(bias); cudaFree(thr); cudaFree(tap_popc);
-    wt = nullptr; mul = bias = nullptr; thr = tap_popc = nullptr;
+    cudaFree(wt_nat); cudaFree(wpop);
+    wt = wt_nat = wpop = nullptr; mul = bias = nullptr; thr = tap_popc = nullptr;
   }
 };
 
@@ -144,6 +151,25 @@ int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream
   lce::bconv_kernel<V, OUT><<<grid, lce::kThreads, smem, s>>>(p);
   return launch_check("bconv_kernel");
 }
+template <int V, int OUT>
+int launch_imma_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_OK(cudaFuncSetAttribute(lce::bconv_imma_kernel<V, OUT>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 lce::kIMaxChunkWords * lce::kIBytesPerWord));
+    attr_set = true;
+  }
+  lce::bconv_imma_kernel<V, OUT><<<grid, lce::kIThreads, smem, s>>>(p);
+  return launch_check("bconv_imma_kernel");
+}
+template <int V>
+int launch_imma_v(int out_type, const lce::ConvKParams& p, dim3 grid, size_t smem,
+                  cudaStream_t s) {
+  if (out_type == LCE_OUT_FLOAT) return launch_imma_vo<V, LCE_OUT_FLOAT>(p, grid, smem, s);
+  return launch_imma_vo<V, LCE_OUT_RAW_ACC>(p, grid, smem, s);
+}
+
 template <int V>
 int launch_conv_v(int out_type, const lce::ConvKParams& p, dim3 grid, size_t smem,
                   cudaStream_t s) {
@@ -165,9 +191,24 @@ int launch_conv(const GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
   if (p.M <= 0) return 0;  // empty batch: nothing to do
   const long long m_tiles = (p.M + lce::kBM - 1) / lce::kBM;
   if (m_tiles > INT_MAX) return fail("too many output pixels");
+  if (p.img_words >= (1LL << 31)) return fail("input image too large (>= 2^31 packed words)");
+  if (c.wt_nat != nullptr && p.vec_store) {
+    // experimental int8 tensor-pipe inner product: 128 x 64 tiles, same integer results
+    lce::ConvKParams q = p;
+    q.wt = c.wt_nat; q.wpop = c.wpop;
+    q.Kc_v = c.imma_Kc_v; q.n_chunks = c.imma_chunks;
+    q.res_stage = 0;
+    const size_t ismem = c.imma_smem;
+    dim3 igrid(static_cast<unsigned>((p.M + lce::kIBM - 1) / lce::kIBM),
+               static_cast<unsigned>(c.groups * c.tiles_per_group));
+    switch (c.V) {
+      case 4: return launch_imma_v<4>(c.out_type, q, igrid, ismem, s);
+      case 2: return launch_imma_v<2>(c.out_type, q, igrid, ismem, s);
+      default: return launch_imma_v<1>(c.out_type, q, igrid, ismem, s);
+    }
+  }
   dim3 grid(static_cast<unsigned>(m_tiles), static_cast<unsigned>(c.groups * c.tiles_per_group));
   const size_t smem = c.smem_bytes + (p.res_stage ? lce::kResStageBytes : 0);
-  if (p.img_words >= (1LL << 31)) return fail("input image too large (>= 2^31 packed words)");
   switch (c.V) {
     case 4: return launch_conv_v<4>(c.out_type, p, grid, smem, s);
     case 2: return launch_conv_v<2>(c.out_type, p, grid, smem, s);
@@ -200,8 +241,32 @@ int build_core_weights(GemmCore* c, const int32_t* filter, bool want_tap_popc) {
                           lce::kBN * c->V;
   CUDA_OK(cudaMalloc(&c->wt, total * 4));
   lce::tile_weights_kernel<<<grid_for(total, 256, 1 << 20), 256>>>(
-      d_filter, c->wt, c->cout_pg, c->tiles_per_group, c->taps, c->Cw_pg, c->V, c->Kv, total);
+      d_filter, c->wt, c->cout_pg, c->tiles_per_group, c->taps, c->Cw_pg, c->V, c->Kv, total, 0);
   if (launch_check("tile_weights_kernel")) return 1;
+  // int8 tensor-pipe inner product (lce_b200_imma.cuh) where a plan is eligible: full 64-channel
+  // tiles, float or raw-accumulator output. LCE_B200_BCONV_IMMA=0 keeps every plan on the
+  // XOR + POPC kernel (bench.py reports both).
+  const char* imma_env = getenv("LCE_B200_BCONV_IMMA");  // read per plan: A/B in one process
+  const bool imma_on = !(imma_env && imma_env[0] == '0');
+  if (imma_on && c->cout_pg % lce::kBN == 0 &&
+      (c->out_type == LCE_OUT_FLOAT || c->out_type == LCE_OUT_RAW_ACC)) {
+    const long long Kw = static_cast<long long>(c->taps) * c->Cw_pg;
+    const long long xtotal = static_cast<long long>(c->groups) * c->tiles_per_group * Kw * 256;
+    CUDA_OK(cudaMalloc(&c->wt_nat, xtotal * 8));
+    lce::expand_weights_imma_kernel<<<grid_for(xtotal, 256, 1 << 22), 256>>>(
+        d_filter, reinterpret_cast<uint2*>(c->wt_nat), c->cout_pg, c->tiles_per_group, c->taps,
+        c->Cw_pg, xtotal);
+    if (launch_check("expand_weights_imma_kernel")) return 1;
+    CUDA_OK(cudaMalloc(&c->wpop, static_cast<size_t>(c->cout + lce::kBN) * 4));
+    CUDA_OK(cudaMemset(c->wpop, 0, static_cast<size_t>(c->cout + lce::kBN) * 4));
+    lce::tap_popc_kernel<<<cdiv(c->cout, 256), 256>>>(d_filter, c->wpop, c->cout, 1,
+                                                      c->taps * c->Cw_pg);
+    if (launch_check("tap_popc_kernel")) return 1;
+    const int imax = lce::kIMaxChunkWords / c->V;
+    c->imma_chunks = cdiv(c->Kv, imax);
+    c->imma_Kc_v = cdiv(c->Kv, c->imma_chunks);
+    c->imma_smem = static_cast<size_t>(c->imma_Kc_v) * c->V * lce::kIBytesPerWord;
+  }
   if (want_tap_popc) {
     const size_t n = static_cast<size_t>(c->cout + lce::kBN) * c->taps;
     CUDA_OK(cudaMalloc(&c->tap_popc, n * 4));

@@ -88,6 +88,7 @@ struct ConvKParams {
   int vec_store;     // output rows are 16B-aligned for this thread's 8 channels
   int bp_fast;       // bitpacked output: tiles start on a 32-channel boundary
   int res_stage;     // residual rows are staged through shared memory (kResStageBytes extra)
+  const int32_t* wpop;  // IMMA path: popcount of each channel's whole filter row
   FastDiv fd_ohw, fd_ow, fd_cwv, fd_kw, fd_tpg;  // / (OH*OW), / OW, / CwV, / KW, / tiles_per_group
   long long img_words;  // H * W * Cw_total (< 2^31, checked by the host)
 };
@@ -260,12 +261,13 @@ __device__ __forceinline__ void split_pixel(const ConvKParams& p, long long m, l
 
 // Gather one K chunk of the im2col rows of tile `m0` into A_buf[kv - kv0][pixel] with
 // zero-filling cp.async. Thread t handles pixel t % BM and every second k-vector.
-template <int V>
+template <int V, int BM_ = kBM, int NT_ = kThreads>
 __device__ __forceinline__ void gather_tile(const ConvKParams& p, typename VecT<V>::T* A_buf,
                                             long long m0, int g, int kv0, int kv1, int tid) {
   using Vec = typename VecT<V>::T;
-  const int lp = tid & (kBM - 1);
-  const int half = tid / kBM;
+  constexpr int kStep = NT_ / BM_;  // threads per pixel: each takes every kStep-th k-vector
+  const int lp = tid & (BM_ - 1);
+  const int half = tid / BM_;
   const long long gm = m0 + lp;
   const bool pix_valid = gm < p.M;
   int iy0 = 0, ix0 = 0;
@@ -283,8 +285,8 @@ __device__ __forceinline__ void gather_tile(const ConvKParams& p, typename VecT<
   int cv = kv - tap * p.CwV;
   int fy = static_cast<int>(fdiv(static_cast<uint32_t>(tap), p.fd_kw));
   int fx = tap - fy * p.KW;
-  uint32_t dst = smem_u32(A_buf + half * kBM + lp);
-  for (; kv < kv1; kv += 2, dst += 2 * kBM * static_cast<uint32_t>(sizeof(Vec))) {
+  uint32_t dst = smem_u32(A_buf + half * BM_ + lp);
+  for (; kv < kv1; kv += kStep, dst += kStep * BM_ * static_cast<uint32_t>(sizeof(Vec))) {
     const int iy = iy0 + fy * p.dh;
     const int ix = ix0 + fx * p.dw;
     const bool inside = pix_valid && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
@@ -293,7 +295,7 @@ __device__ __forceinline__ void gather_tile(const ConvKParams& p, typename VecT<
     const int off = (iy * p.W + ix) * p.Cw_total + cv * V;
     const int32_t* src = inside ? img + off : p.in;
     cp_async_zfill_u32<V * 4>(dst, src, inside ? V * 4 : 0);
-    cv += 2;
+    cv += kStep;
     while (cv >= p.CwV) {
       cv -= p.CwV;
       if (++fx == p.KW) {
@@ -729,7 +731,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSm) bconv_kernel(const ConvK
 // channels past the group's end. Runs once per plan ("weights are static").
 __global__ void tile_weights_kernel(const int32_t* __restrict__ filter, int32_t* __restrict__ wt,
                                     int cout_pg, int tiles_per_group, int taps, int Cw_pg, int V,
-                                    int Kv, long long total) {
+                                    int Kv, long long total, int natural_order) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
   const int v = static_cast<int>(idx % V);
@@ -739,7 +741,7 @@ __global__ void tile_weights_kernel(const int32_t* __restrict__ filter, int32_t*
   const int kv = static_cast<int>(r % Kv);
   const int nt = static_cast<int>(r / Kv);
   const int g = nt / tiles_per_group, tg = nt - g * tiles_per_group;
-  const int ch = tg * kBN + (pos & 7) * 8 + (pos >> 3);
+  const int ch = tg * kBN + (natural_order ? pos : (pos & 7) * 8 + (pos >> 3));
   int32_t val = 0;
   if (ch < cout_pg) {
     const int CwV = Cw_pg / V;

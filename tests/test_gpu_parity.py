@@ -317,3 +317,56 @@ def test_bconv_fused_residual_and_pack_entry_point(capi):
         assert_same_bits(out.cpu().numpy(), want, "fused sum")
         assert_same_bits(packed.cpu().numpy(), L.quantize(want), "fused packed signs")
         plan.close()
+
+
+@pytest.mark.parametrize("imma", ["0", "1"])
+def test_bconv_both_inner_products_vs_oracle(capi, imma, monkeypatch):
+    """The XOR+POPC kernel (LCE_B200_BCONV_IMMA=0) and the int8 tensor-pipe kernel (default where
+    a plan has full 64-channel tiles and float / raw output) produce the reference's integers:
+    ones / zero padding, stride, dilation, groups, multi-chunk K, ragged M, fused tail."""
+    import ctypes as C
+    monkeypatch.setenv("LCE_B200_BCONV_IMMA", imma)
+    rng = np.random.default_rng(77)
+    grid = [
+        # b, h, w, cin, fh, fw, cout, groups, stride, dilation, padding, pad_value, act
+        (2, 14, 14, 64, 3, 3, 64, 1, (1, 1), (1, 1), L.PADDING_SAME, 1, L.ACT_RELU),
+        (1, 7, 7, 512, 3, 3, 128, 1, (1, 1), (1, 1), L.PADDING_SAME, 1, L.ACT_NONE),
+        (3, 9, 11, 64, 3, 3, 64, 1, (1, 1), (1, 1), L.PADDING_SAME, 0, L.ACT_NONE),
+        (2, 13, 9, 128, 3, 3, 192, 1, (2, 2), (1, 1), L.PADDING_SAME, 0, L.ACT_NONE),
+        (2, 12, 12, 96, 3, 2, 64, 1, (1, 2), (2, 1), L.PADDING_VALID, 1, L.ACT_RELU6),
+        (2, 10, 10, 128, 3, 3, 128, 2, (1, 1), (1, 1), L.PADDING_SAME, 1, L.ACT_RELU),
+        (1, 5, 5, 1024, 5, 5, 64, 1, (1, 1), (1, 1), L.PADDING_SAME, 1, L.ACT_NONE),   # K = 800 words
+        (5, 6, 6, 32, 1, 1, 64, 1, (1, 1), (1, 1), L.PADDING_VALID, 1, L.ACT_RELU_N1_TO_1),
+    ]
+    for n, (b, h, w, cin, fh, fw, co, g, st, dl, pad, pv, act) in enumerate(grid):
+        case = L.make_bconv_case(9000 + n, b, h, w, cin, fh, fw, co, g, st, dl, pad, pv, act,
+                                 L.OUT_FLOAT)
+        want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr)
+        assert_same_bits(run_gpu_bconv(capi, case), want, f"imma={imma} case {n}")
+        # fused tail on the same plan shape
+        plan = capi.BConv2d(gpu_desc(capi, case.desc), case.filt, case.mul, case.bias)
+        res = rng.standard_normal(want.shape).astype(np.float32)
+        out = torch.empty(want.shape, device="cuda")
+        packed = torch.empty(want.shape[:3] + (L.cdiv(co, 32),), dtype=torch.int32, device="cuda")
+        d_in, d_res = dev(case.inp), dev(res)
+        rc = capi.lib().lce_b200_bconv2d_run_fused(
+            plan._h, C.c_void_p(d_in.data_ptr()), C.c_void_p(d_res.data_ptr()),
+            C.c_int(L.ACT_RELU if n % 2 else L.ACT_NONE), C.c_void_p(out.data_ptr()),
+            C.c_void_p(packed.data_ptr() if g == 1 else 0),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, capi.lib().lce_b200_last_error()
+        torch.cuda.synchronize()
+        ws = (want + res).astype(np.float32)
+        if n % 2:
+            ws = np.maximum(ws, 0)
+        assert_same_bits(out.cpu().numpy(), ws, f"imma={imma} fused sum {n}")
+        if g == 1:
+            assert_same_bits(packed.cpu().numpy(), L.quantize(ws), f"imma={imma} fused signs {n}")
+        plan.close()
+    # plain BGEMM, raw accumulators
+    A = rng.integers(-2**31, 2**31 - 1, (333, 24), dtype=np.int64).astype(np.int32)
+    W = rng.integers(-2**31, 2**31 - 1, (128, 24), dtype=np.int64).astype(np.int32)
+    gemm = capi.BGemm(dev(W))
+    got = gemm(dev(A)).cpu().numpy()
+    gemm.close()
+    assert np.array_equal(got, L.bgemm(A, W, threads=4))
