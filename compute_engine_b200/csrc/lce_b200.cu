@@ -157,7 +157,7 @@ int launch_imma_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream
   if (!attr_set) {
     CUDA_OK(cudaFuncSetAttribute(lce::bconv_imma_kernel<V, OUT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 lce::kIMaxChunkWords * lce::kIBytesPerWord));
+                                 2 * lce::kIMaxChunkWords * lce::kIBytesPerWord));
     attr_set = true;
   }
   lce::bconv_imma_kernel<V, OUT><<<grid, lce::kIThreads, smem, s>>>(p);
@@ -265,7 +265,8 @@ int build_core_weights(GemmCore* c, const int32_t* filter, bool want_tap_popc) {
     const int imax = lce::kIMaxChunkWords / c->V;
     c->imma_chunks = cdiv(c->Kv, imax);
     c->imma_Kc_v = cdiv(c->Kv, c->imma_chunks);
-    c->imma_smem = static_cast<size_t>(c->imma_Kc_v) * c->V * lce::kIBytesPerWord;
+    c->imma_smem = static_cast<size_t>(c->imma_Kc_v) * c->V * lce::kIBytesPerWord *
+                   (c->imma_chunks > 1 ? 2 : 1);  // two-deep ring
   }
   if (want_tap_popc) {
     const size_t n = static_cast<size_t>(c->cout + lce::kBN) * c->taps;

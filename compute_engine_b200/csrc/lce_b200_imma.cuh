@@ -30,7 +30,13 @@ constexpr int kIBM = 128;
 constexpr int kIThreads = 128;
 constexpr int kICtasPerSm = 3;
 constexpr int kIBytesPerWord = kIBM * 4 + 8 * 32 * 8;  // smem per K word: packed A column + B fragments
-constexpr int kIMaxChunkWords = 28;                   // 28 * 2560 B = 70 KiB per CTA, 3 CTAs per SM
+#ifndef LCE_IMMA_CHUNK
+#define LCE_IMMA_CHUNK 14
+#endif
+// K is staged in chunks through a TWO-deep ring: chunk c+1 is gathered / TMA-copied while chunk c
+// is multiplied (the resident CTAs of an SM start together and stay in lock-step, so overlap has
+// to come from inside the CTA). 2 x 14 x 2560 B = 70 KiB per CTA, 3 CTAs per SM.
+constexpr int kIMaxChunkWords = LCE_IMMA_CHUNK;
 
 // byte `tig` of w -> two registers of four u8 each: bit i of the low / high nibble -> byte i
 __device__ __forceinline__ void expand01(uint32_t w, uint32_t sel, uint32_t& lo, uint32_t& hi) {
@@ -248,9 +254,8 @@ template <int V, int OUT>
 __global__ void __launch_bounds__(kIThreads, kICtasPerSm) bconv_imma_kernel(const ConvKParams p) {
   using Vec = typename VecT<V>::T;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  Vec* A_s = reinterpret_cast<Vec*>(smem_raw);                                  // [Kc_v][128]
-  uint2* B_s = reinterpret_cast<uint2*>(A_s + static_cast<size_t>(p.Kc_v) * kIBM);  // [Kc_v*V][8][32]
-  __shared__ __align__(8) uint64_t wbar;
+  // two buffers of { A: [Kc_v][128] packed vectors, B: [Kc_v*V][8][32] int8 fragments }
+  __shared__ __align__(8) uint64_t wbar[2];
 
   const int tid = threadIdx.x;
   const int warp = tid >> 5, lane = tid & 31;
@@ -262,7 +267,8 @@ __global__ void __launch_bounds__(kIThreads, kICtasPerSm) bconv_imma_kernel(cons
   const int c_tile = g * p.cout_pg + tg * kBN;
 
   if (tid == 0) {
-    mbar_init(&wbar, 1);
+    mbar_init(&wbar[0], 1);
+    mbar_init(&wbar[1], 1);
     fence_barrier_init();
   }
   __syncthreads();
@@ -286,24 +292,48 @@ __global__ void __launch_bounds__(kIThreads, kICtasPerSm) bconv_imma_kernel(cons
     }
   }
 
-  uint32_t phase = 0;
-  for (int ch = 0; ch < p.n_chunks; ++ch) {
+  const size_t chunk_bytes = static_cast<size_t>(p.Kc_v) * V * kIBytesPerWord;
+  auto stage = [&](int ch) {
+    unsigned char* base = smem_raw + (ch & 1) * chunk_bytes;
+    Vec* A_b = reinterpret_cast<Vec*>(base);
+    uint2* B_b = reinterpret_cast<uint2*>(A_b + static_cast<size_t>(p.Kc_v) * kIBM);
     const int kv0 = ch * p.Kc_v;
     const int kv1 = min(kv0 + p.Kc_v, p.Kv);
     if (tid == 0) {
       const uint32_t bytes = static_cast<uint32_t>(kv1 - kv0) * V * (8 * 32 * 8);
-      mbar_arrive_expect_tx(&wbar, bytes);
-      bulk_g2s(B_s, reinterpret_cast<const uint2*>(p.wt) +
+      mbar_arrive_expect_tx(&wbar[ch & 1], bytes);
+      bulk_g2s(B_b, reinterpret_cast<const uint2*>(p.wt) +
                         (static_cast<size_t>(nt) * p.Kv + kv0) * V * (8 * 32),
-               bytes, &wbar);
+               bytes, &wbar[ch & 1]);
     }
-    gather_tile<V, kIBM, kIThreads>(p, A_s, m0, g, kv0, kv1, tid);
-    cp_async_wait_all();
-    mbar_wait(&wbar, phase);
-    phase ^= 1u;
+    gather_tile<V, kIBM, kIThreads>(p, A_b, m0, g, kv0, kv1, tid);
+    cp_async_commit();
+  };
+  stage(0);
+#ifdef LCE_IMMA_EXP_NOLOAD   // timing experiment only (wrong results): no loads after chunk 0
+  asm volatile("cp.async.wait_group 0;" ::: "memory");
+  mbar_wait(&wbar[0], 0);
+  __syncthreads();
+#endif
+  for (int ch = 0; ch < p.n_chunks; ++ch) {
+    const bool more = ch + 1 < p.n_chunks;
+#ifndef LCE_IMMA_EXP_NOLOAD
+    if (more) stage(ch + 1);  // its buffer was released by the barrier that ended chunk ch - 1
+    if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else asm volatile("cp.async.wait_group 0;" ::: "memory");
+    mbar_wait(&wbar[ch & 1], (ch >> 1) & 1);
     __syncthreads();
-    compute_chunk_imma<V>(A_s, B_s, kv1 - kv0, warp, gid, tig, lane, acc);
+#elif !defined(LCE_IMMA_EXP_NOSYNC)
     __syncthreads();
+#endif
+    unsigned char* base = smem_raw + (ch & 1) * chunk_bytes;
+    const Vec* A_b = reinterpret_cast<const Vec*>(base);
+    const uint2* B_b = reinterpret_cast<const uint2*>(A_b + static_cast<size_t>(p.Kc_v) * kIBM);
+    const int kv0 = ch * p.Kc_v;
+    compute_chunk_imma<V>(A_b, B_b, min(kv0 + p.Kc_v, p.Kv) - kv0, warp, gid, tig, lane, acc);
+#ifndef LCE_IMMA_EXP_NOSYNC
+    __syncthreads();
+#endif
   }
   if (p.tap_popc != nullptr) zero_pad_correction_imma(p, acc, m0, c_tile, warp, gid, tig);
   epilogue_imma<OUT>(p, acc, m0, c_tile, warp, gid, tig);
