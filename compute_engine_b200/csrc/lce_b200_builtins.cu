@@ -6,6 +6,7 @@
 // fully_connected.h:29, softmax.h:31, reduce.h); fp32 accumulate with FMA.
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cfloat>
 #include <climits>
 #include <cstdint>
@@ -68,13 +69,12 @@ constexpr int kDirectGroupStride = 20;   // 16 + 4 floats: conflict-free LDS.128
 // Each thread computes kPX pixels x 16 channels so every 128-bit weight read from shared
 // memory feeds 4*kPX FMAs (with one pixel per thread the kernel was LDS-bound: ncu showed
 // short-scoreboard / MIO-throttle stalls dominating).
-constexpr int kPX = 4;
-template <int KH_, int KW_, int CIN_>
+template <int KH_, int KW_, int CIN_, int kPX>
 __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ filter,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ out, ConvGeom g,
-                                                            long long M, int G) {
+                                                            long long M, int G, int tiles_per_block) {
   extern __shared__ __align__(16) float w_s[];   // [K][G][20] then bias [G][16]
   const int KH = KH_ ? KH_ : g.KH, KW = KW_ ? KW_ : g.KW, CIN = CIN_ ? CIN_ : g.Cin;
   const int K = KH * KW * CIN;
@@ -95,8 +95,11 @@ __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restr
   const unsigned lpx = threadIdx.x / static_cast<unsigned>(G);
   const int gi = static_cast<int>(threadIdx.x - lpx * G);
   if (lpx >= px_per_blk) return;
-  const unsigned blk_m0 = blockIdx.x * px_per_blk * kPX;
   const unsigned ohw = g.OH * g.OW;
+  // the weights staged above serve `tiles_per_block` consecutive pixel tiles
+  for (int tile = 0; tile < tiles_per_block; ++tile) {
+  const unsigned blk_m0 = (blockIdx.x * tiles_per_block + tile) * px_per_blk * kPX;
+  if (blk_m0 >= static_cast<unsigned>(M)) break;
   long long ibase[kPX];
   int iy0[kPX], ix0[kPX];
   bool ok[kPX];
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restr
       for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[p][c] + bb[c], g.act);
     }
   }
+  }  // tile
 }
 
 // ---- plain-GEMM convolution (1x1, stride 1: A = [M, K] row-major): 128x128x16 tiles, 8x8
@@ -710,24 +714,47 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
     if (smem > 48 * 1024) {
       static bool attr = false;
       if (!attr) {
-        cudaFuncSetAttribute(conv_direct16_kernel<0, 0, 0>,
+        cudaFuncSetAttribute(conv_direct16_kernel<0, 0, 0, 4>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr = true;
       }
     }
-    // 128 threads = (128 / G) pixels x G groups, kPX pixels each
+    // 128 threads = (128 / G) pixels x G groups, PX pixels each. PX trades shared-memory weight
+    // reads per FMA against registers / resident warps: the two compile-time shapes are latency
+    // bound at PX = 4 (236 / 130 registers, 12-18 % of the warp slots); measured best: stem PX = 2.
+    static const int px_env = [] {
+      const char* e = getenv("LCE_B200_DIRECT_PX");
+      return e ? atoi(e) : 0;
+    }();
+    const bool stem = g.KH == 3 && g.KW == 3 && g.Cin == 3;
+    const bool pw16 = g.KH == 1 && g.KW == 1 && g.Cin == 16 && !((uintptr_t)in & 15);
+    int PX = stem ? 2 : 4;
+    if ((stem || pw16) && (px_env == 1 || px_env == 2 || px_env == 4)) PX = px_env;
     const int px_per_blk = 128 / G;
-    const unsigned blocks = static_cast<unsigned>((M + px_per_blk * kPX - 1) / (px_per_blk * kPX));
+    const long long tiles = (M + px_per_blk * PX - 1) / (px_per_blk * PX);
+    // the pointwise 16 -> 64 layer stages 4 KB of weights per block for only 128 pixels: give a
+    // block 8 tiles (measured 0.125 -> 0.109 ms); the stem is better off with more, smaller
+    // blocks (0.168 -> 0.132 ms at PX = 2, one tile per block)
+    const int tpb = pw16 ? static_cast<int>(std::max<long long>(
+                               1, std::min<long long>(8, tiles / (148 * 8))))
+                         : 1;
+    const unsigned blocks = static_cast<unsigned>((tiles + tpb - 1) / tpb);
     (void)threads;
-    if (g.KH == 3 && g.KW == 3 && g.Cin == 3)
-      conv_direct16_kernel<3, 3, 3><<<blocks, 128, smem, as_stream(stream)>>>(in, filter, bias, out,
-                                                                              g, M, G);
-    else if (g.KH == 1 && g.KW == 1 && g.Cin == 16 && !((uintptr_t)in & 15))
-      conv_direct16_kernel<1, 1, 16><<<blocks, 128, smem, as_stream(stream)>>>(in, filter, bias,
-                                                                               out, g, M, G);
-    else
-      conv_direct16_kernel<0, 0, 0><<<blocks, 128, smem, as_stream(stream)>>>(in, filter, bias, out,
-                                                                              g, M, G);
+    cudaStream_t st = as_stream(stream);
+#define LCE_DIRECT(KH_, KW_, CIN_, PX_) \
+  conv_direct16_kernel<KH_, KW_, CIN_, PX_><<<blocks, 128, smem, st>>>(in, filter, bias, out, g, M, G, tpb)
+    if (stem) {
+      if (PX == 1) LCE_DIRECT(3, 3, 3, 1);
+      else if (PX == 2) LCE_DIRECT(3, 3, 3, 2);
+      else LCE_DIRECT(3, 3, 3, 4);
+    } else if (pw16) {
+      if (PX == 1) LCE_DIRECT(1, 1, 16, 1);
+      else if (PX == 2) LCE_DIRECT(1, 1, 16, 2);
+      else LCE_DIRECT(1, 1, 16, 4);
+    } else {
+      LCE_DIRECT(0, 0, 0, 4);
+    }
+#undef LCE_DIRECT
     return launch_check("conv_direct16_kernel");
   }
   const bool plain = g.KH == 1 && g.KW == 1 && g.sh == 1 && g.sw == 1 && (K & 3) == 0 &&
