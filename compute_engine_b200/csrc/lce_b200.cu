@@ -151,13 +151,18 @@ int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream
   lce::bconv_kernel<V, OUT><<<grid, lce::kThreads, smem, s>>>(p);
   return launch_check("bconv_kernel");
 }
+size_t imma_smem_budget(int V) {
+  const int ctas = lce::imma_ctas_per_sm(V);
+  return (227u * 1024u / ctas - 1024u - 256u) & ~size_t{127};
+}
+
 template <int V, int OUT>
 int launch_imma_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_OK(cudaFuncSetAttribute(lce::bconv_imma_kernel<V, OUT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 2 * lce::kIMaxChunkWords * lce::kIBytesPerWord));
+                                 static_cast<int>(imma_smem_budget(V))));
     attr_set = true;
   }
   lce::bconv_imma_kernel<V, OUT><<<grid, lce::kIThreads, smem, s>>>(p);
@@ -262,8 +267,12 @@ int build_core_weights(GemmCore* c, const int32_t* filter, bool want_tap_popc) {
     lce::tap_popc_kernel<<<cdiv(c->cout, 256), 256>>>(d_filter, c->wpop, c->cout, 1,
                                                       c->taps * c->Cw_pg);
     if (launch_check("tap_popc_kernel")) return 1;
-    const int imax = lce::kIMaxChunkWords / c->V;
-    c->imma_chunks = cdiv(c->Kv, imax);
+    // K staging: everything in one chunk when it fits the CTA's shared-memory share, else a
+    // two-deep ring of equal chunks. 3 CTAs per SM for uint4 operands, 4 otherwise (registers).
+    const size_t budget = imma_smem_budget(c->V);
+    const int single_max = static_cast<int>(budget / lce::kIBytesPerWord) / c->V;      // vectors
+    const int ring_max = static_cast<int>(budget / (2 * lce::kIBytesPerWord)) / c->V;
+    c->imma_chunks = c->Kv <= single_max ? 1 : cdiv(c->Kv, std::max(ring_max, 1));
     c->imma_Kc_v = cdiv(c->Kv, c->imma_chunks);
     c->imma_smem = static_cast<size_t>(c->imma_Kc_v) * c->V * lce::kIBytesPerWord *
                    (c->imma_chunks > 1 ? 2 : 1);  // two-deep ring

@@ -1,5 +1,9 @@
-// lce_b200_imma.cuh -- EXPERIMENTAL alternative inner product for the binary convolution
-// (opt-in, LCE_B200_BCONV_IMMA=1; the default path is the XOR + POPC kernel north_star names).
+// lce_b200_imma.cuh -- the binary convolution's inner product on the int8 tensor pipe.
+// Used for every plan with full 64-channel tiles and float / raw-accumulator output (the three
+// model families' LceBconv2d layers, the BGEMM sweep); everything else, and every plan when
+// LCE_B200_BCONV_IMMA=0, runs the XOR + POPC kernel of lce_b200_kernels.cuh that north_star
+// describes. Both produce the reference's integers bit for bit (tests/test_gpu_parity.py runs
+// the same cases through both); bench.py reports both.
 //
 // sm_100a has no b1 tensor instruction (ptxas lowers mma.sync ... b1 to masked int8 IMMAs that
 // are no faster than the carry-save tree: profiles/r01_microbench_mma.jsonl), but the legacy
@@ -28,15 +32,16 @@ namespace lce {
 
 constexpr int kIBM = 128;
 constexpr int kIThreads = 128;
-constexpr int kICtasPerSm = 3;
-constexpr int kIBytesPerWord = kIBM * 4 + 8 * 32 * 8;  // smem per K word: packed A column + B fragments
-#ifndef LCE_IMMA_CHUNK
-#define LCE_IMMA_CHUNK 14
+// resident CTAs per SM the kernel is compiled for (register cap 65536 / (128 * n))
+#ifdef LCE_IMMA_ALL4
+__host__ __device__ constexpr int imma_ctas_per_sm(int) { return 4; }
+#else
+__host__ __device__ constexpr int imma_ctas_per_sm(int V) { return V == 4 ? 3 : 4; }
 #endif
-// K is staged in chunks through a TWO-deep ring: chunk c+1 is gathered / TMA-copied while chunk c
-// is multiplied (the resident CTAs of an SM start together and stay in lock-step, so overlap has
-// to come from inside the CTA). 2 x 14 x 2560 B = 70 KiB per CTA, 3 CTAs per SM.
-constexpr int kIMaxChunkWords = LCE_IMMA_CHUNK;
+constexpr int kIBytesPerWord = kIBM * 4 + 8 * 32 * 8;  // smem per K word: packed A column + B fragments
+// K is staged in one chunk when it fits, else through a TWO-deep ring: chunk c+1 is gathered /
+// TMA-copied while chunk c is multiplied. The host sizes the chunks (imma_smem_budget):
+// 3 CTAs per SM for the uint4 instances (153 registers), 4 for the narrower ones (128).
 
 // byte `tig` of w -> two registers of four u8 each: bit i of the low / high nibble -> byte i
 __device__ __forceinline__ void expand01(uint32_t w, uint32_t sel, uint32_t& lo, uint32_t& hi) {
@@ -91,25 +96,32 @@ __device__ __forceinline__ void compute_chunk_imma(const typename VecT<V>::T* A_
   const uint2* b_base = B_s + lane;
 #pragma unroll 1
   for (int kv = 0; kv < nkv; ++kv) {
-    uint32_t a[V][2][4];
+    uint32_t r[2][2][V];   // [m sub-tile][row gid / gid + 8][word]
 #pragma unroll
     for (int ms = 0; ms < 2; ++ms) {
-      uint32_t r0[V], r1[V];
-      load_words<V>(a_base + kv * kIBM + ms * 16, r0);       // row gid
-      load_words<V>(a_base + kv * kIBM + ms * 16 + 8, r1);   // row gid + 8
-#pragma unroll
-      for (int q = 0; q < V; ++q) {
-        expand01(r0[q], sel, a[q][ms][0], a[q][ms][2]);
-        expand01(r1[q], sel, a[q][ms][1], a[q][ms][3]);
-      }
+      load_words<V>(a_base + kv * kIBM + ms * 16, r[ms][0]);
+      load_words<V>(a_base + kv * kIBM + ms * 16 + 8, r[ms][1]);
     }
+    // two k-steps at a time: 16 live fragment registers instead of 8 * V
+    constexpr int H = V < 2 ? V : 2;
 #pragma unroll
-    for (int q = 0; q < V; ++q) {
+    for (int qh = 0; qh < V; qh += H) {
+      uint32_t a[H][2][4];
 #pragma unroll
-      for (int ns = 0; ns < 8; ++ns) {
-        const uint2 b = b_base[((kv * V + q) * 8 + ns) * 32];
-        mma_u8s8(acc[0][ns], a[q][0], b.x, b.y);
-        mma_u8s8(acc[1][ns], a[q][1], b.x, b.y);
+      for (int q = 0; q < H; ++q)
+#pragma unroll
+        for (int ms = 0; ms < 2; ++ms) {
+          expand01(r[ms][0][qh + q], sel, a[q][ms][0], a[q][ms][2]);
+          expand01(r[ms][1][qh + q], sel, a[q][ms][1], a[q][ms][3]);
+        }
+#pragma unroll
+      for (int q = 0; q < H; ++q) {
+#pragma unroll
+        for (int ns = 0; ns < 8; ++ns) {
+          const uint2 b = b_base[((kv * V + qh + q) * 8 + ns) * 32];
+          mma_u8s8(acc[0][ns], a[q][0], b.x, b.y);
+          mma_u8s8(acc[1][ns], a[q][1], b.x, b.y);
+        }
       }
     }
   }
@@ -251,7 +263,8 @@ __device__ __forceinline__ void epilogue_imma(const ConvKParams& p, int (&acc)[2
 }
 
 template <int V, int OUT>
-__global__ void __launch_bounds__(kIThreads, kICtasPerSm) bconv_imma_kernel(const ConvKParams p) {
+__global__ void __launch_bounds__(kIThreads, imma_ctas_per_sm(V))
+bconv_imma_kernel(const ConvKParams p) {
   using Vec = typename VecT<V>::T;
   extern __shared__ __align__(128) unsigned char smem_raw[];
   // two buffers of { A: [Kc_v][128] packed vectors, B: [Kc_v*V][8][32] int8 fragments }
@@ -310,30 +323,19 @@ __global__ void __launch_bounds__(kIThreads, kICtasPerSm) bconv_imma_kernel(cons
     cp_async_commit();
   };
   stage(0);
-#ifdef LCE_IMMA_EXP_NOLOAD   // timing experiment only (wrong results): no loads after chunk 0
-  asm volatile("cp.async.wait_group 0;" ::: "memory");
-  mbar_wait(&wbar[0], 0);
-  __syncthreads();
-#endif
   for (int ch = 0; ch < p.n_chunks; ++ch) {
     const bool more = ch + 1 < p.n_chunks;
-#ifndef LCE_IMMA_EXP_NOLOAD
     if (more) stage(ch + 1);  // its buffer was released by the barrier that ended chunk ch - 1
     if (more) asm volatile("cp.async.wait_group 1;" ::: "memory");
     else asm volatile("cp.async.wait_group 0;" ::: "memory");
     mbar_wait(&wbar[ch & 1], (ch >> 1) & 1);
     __syncthreads();
-#elif !defined(LCE_IMMA_EXP_NOSYNC)
-    __syncthreads();
-#endif
     unsigned char* base = smem_raw + (ch & 1) * chunk_bytes;
     const Vec* A_b = reinterpret_cast<const Vec*>(base);
     const uint2* B_b = reinterpret_cast<const uint2*>(A_b + static_cast<size_t>(p.Kc_v) * kIBM);
     const int kv0 = ch * p.Kc_v;
     compute_chunk_imma<V>(A_b, B_b, min(kv0 + p.Kc_v, p.Kv) - kv0, warp, gid, tig, lane, acc);
-#ifndef LCE_IMMA_EXP_NOSYNC
     __syncthreads();
-#endif
   }
   if (p.tap_popc != nullptr) zero_pad_correction_imma(p, acc, m0, c_tile, warp, gid, tig);
   epilogue_imma<OUT>(p, acc, m0, c_tile, warp, gid, tig);
