@@ -69,7 +69,7 @@ constexpr int kDirectGroupStride = 20;   // 16 + 4 floats: conflict-free LDS.128
 // Each thread computes kPX pixels x 16 channels so every 128-bit weight read from shared
 // memory feeds 4*kPX FMAs (with one pixel per thread the kernel was LDS-bound: ncu showed
 // short-scoreboard / MIO-throttle stalls dominating).
-template <int KH_, int KW_, int CIN_, int kPX>
+template <int KH_, int KW_, int CIN_, int kPX, bool kTileLoop = false>
 __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restrict__ in,
                                                             const float* __restrict__ filter,
                                                             const float* __restrict__ bias,
@@ -97,8 +97,9 @@ __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restr
   if (lpx >= px_per_blk) return;
   const unsigned ohw = g.OH * g.OW;
   // the weights staged above serve `tiles_per_block` consecutive pixel tiles
-  for (int tile = 0; tile < tiles_per_block; ++tile) {
-  const unsigned blk_m0 = (blockIdx.x * tiles_per_block + tile) * px_per_blk * kPX;
+  const int n_tile = kTileLoop ? tiles_per_block : 1;
+  for (int tile = 0; tile < n_tile; ++tile) {
+  const unsigned blk_m0 = (blockIdx.x * n_tile + tile) * px_per_blk * kPX;
   if (blk_m0 >= static_cast<unsigned>(M)) break;
   long long ibase[kPX];
   int iy0[kPX], ix0[kPX];
@@ -494,12 +495,12 @@ __global__ void __launch_bounds__(256) pool_v4_kernel(const float4* __restrict__
 // one output pixel x 4 channels; the 4x4 input window is loaded once (16 x LDG.128), the nine
 // pooled values are formed in registers and multiplied in the same (fy, fx) order as
 // depthwise_v4_kernel, so the result is bit-identical to the two-kernel sequence.
-__global__ void __launch_bounds__(256) pool2_dw3_v4_kernel(const float4* __restrict__ in,
-                                                           const float4* __restrict__ filter,
-                                                           const float4* __restrict__ bias,
-                                                           float4* __restrict__ out, int H, int W,
-                                                           int C4, int PH, int PW, int OH, int OW,
-                                                           int sh, int sw, int ph, int pw, int act) {
+__global__ void __launch_bounds__(256, 4) pool2_dw3_v4_kernel(const float4* __restrict__ in,
+                                                              const float4* __restrict__ filter,
+                                                              const float4* __restrict__ bias,
+                                                              float4* __restrict__ out, int H, int W,
+                                                              int C4, int PH, int PW, int OH, int OW,
+                                                              int sh, int sw, int ph, int pw, int act) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= OW * C4) return;
   const int ox = i / C4, c = i - ox * C4;
@@ -508,36 +509,46 @@ __global__ void __launch_bounds__(256) pool2_dw3_v4_kernel(const float4* __restr
   const int y0 = oy * sh - ph, x0 = ox * sw - pw;   // top-left pooled coordinate of the window
   const float4* img = in + b * H * W * C4 + c;
   const float4 lowest = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
-  float4 v[4][4];
+  auto vmax = [](const float4& a, const float4& q) {
+    return make_float4(fmaxf(a.x, q.x), fmaxf(a.y, q.y), fmaxf(a.z, q.z), fmaxf(a.w, q.w));
+  };
+  // Row by row (one input row of 4 pixels live at a time: half the registers of holding the
+  // 4 x 4 window, so twice the resident warps): h[x] = max(v[x], v[x+1]) per input row, a pooled
+  // row is max(h of two consecutive input rows). max is exact in any order; the final
+  // max(lowest, .) reproduces pool_v4_kernel's result for an all-NaN window too.
+  bool xin[4];
 #pragma unroll
-  for (int dy = 0; dy < 4; ++dy)
-#pragma unroll
-    for (int dx = 0; dx < 4; ++dx) {
-      const int y = y0 + dy, x = x0 + dx;
-      const bool ok = static_cast<unsigned>(y) < static_cast<unsigned>(H) &&
-                      static_cast<unsigned>(x) < static_cast<unsigned>(W);
-      v[dy][dx] = ok ? __ldg(img + (static_cast<long long>(y) * W + x) * C4) : lowest;
-    }
+  for (int dx = 0; dx < 4; ++dx) xin[dx] = static_cast<unsigned>(x0 + dx) < static_cast<unsigned>(W);
+  float4 hp[3];   // h of the previous input row
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-  for (int fy = 0; fy < 3; ++fy) {
-    const int py = y0 + fy;
-    if (static_cast<unsigned>(py) >= static_cast<unsigned>(PH)) continue;
+  for (int dy = 0; dy < 4; ++dy) {
+    const int y = y0 + dy;
+    const bool yin = static_cast<unsigned>(y) < static_cast<unsigned>(H);
+    const float4* row = img + (static_cast<long long>(y) * W + x0) * C4;
+    float4 v[4];
 #pragma unroll
-    for (int fx = 0; fx < 3; ++fx) {
-      const int px = x0 + fx;
-      if (static_cast<unsigned>(px) >= static_cast<unsigned>(PW)) continue;
-      // pool_v4_kernel's order: (y, x), (y, x+1), (y+1, x), (y+1, x+1)
-      float4 m = lowest;
-      const float4 e0 = v[fy][fx], e1 = v[fy][fx + 1], e2 = v[fy + 1][fx], e3 = v[fy + 1][fx + 1];
-      m.x = fmaxf(fmaxf(fmaxf(fmaxf(m.x, e0.x), e1.x), e2.x), e3.x);
-      m.y = fmaxf(fmaxf(fmaxf(fmaxf(m.y, e0.y), e1.y), e2.y), e3.y);
-      m.z = fmaxf(fmaxf(fmaxf(fmaxf(m.z, e0.z), e1.z), e2.z), e3.z);
-      m.w = fmaxf(fmaxf(fmaxf(fmaxf(m.w, e0.w), e1.w), e2.w), e3.w);
-      const float4 w = __ldg(filter + (fy * 3 + fx) * C4 + c);
-      acc.x = fmaf(m.x, w.x, acc.x); acc.y = fmaf(m.y, w.y, acc.y);
-      acc.z = fmaf(m.z, w.z, acc.z); acc.w = fmaf(m.w, w.w, acc.w);
+    for (int dx = 0; dx < 4; ++dx) v[dx] = (yin && xin[dx]) ? __ldg(row + dx * C4) : lowest;
+    float4 h[3];
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) h[dx] = vmax(v[dx], v[dx + 1]);
+    if (dy > 0) {
+      const int fy = dy - 1;
+      const int py = y0 + fy;
+      if (static_cast<unsigned>(py) < static_cast<unsigned>(PH)) {
+#pragma unroll
+        for (int fx = 0; fx < 3; ++fx) {
+          const int px = x0 + fx;
+          if (static_cast<unsigned>(px) >= static_cast<unsigned>(PW)) continue;
+          const float4 m = vmax(lowest, vmax(hp[fx], h[fx]));
+          const float4 w = __ldg(filter + (fy * 3 + fx) * C4 + c);
+          acc.x = fmaf(m.x, w.x, acc.x); acc.y = fmaf(m.y, w.y, acc.y);
+          acc.z = fmaf(m.z, w.z, acc.z); acc.w = fmaf(m.w, w.w, acc.w);
+        }
+      }
     }
+#pragma unroll
+    for (int dx = 0; dx < 3; ++dx) hp[dx] = h[dx];
   }
   float4 bb = make_float4(0.f, 0.f, 0.f, 0.f);
   if (bias) bb = __ldg(bias + c);
@@ -735,9 +746,9 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
     // the pointwise 16 -> 64 layer stages 4 KB of weights per block for only 128 pixels: give a
     // block 8 tiles (measured 0.125 -> 0.109 ms); the stem is better off with more, smaller
     // blocks (0.168 -> 0.132 ms at PX = 2, one tile per block)
-    const int tpb = pw16 ? static_cast<int>(std::max<long long>(
-                               1, std::min<long long>(8, tiles / (148 * 8))))
-                         : 1;
+    const int tpb = (pw16 && PX == 4) ? static_cast<int>(std::max<long long>(
+                                            1, std::min<long long>(8, tiles / (148 * 8))))
+                                      : 1;
     const unsigned blocks = static_cast<unsigned>((tiles + tpb - 1) / tpb);
     (void)threads;
     cudaStream_t st = as_stream(stream);
@@ -750,7 +761,9 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
     } else if (pw16) {
       if (PX == 1) LCE_DIRECT(1, 1, 16, 1);
       else if (PX == 2) LCE_DIRECT(1, 1, 16, 2);
-      else LCE_DIRECT(1, 1, 16, 4);
+      else
+        conv_direct16_kernel<1, 1, 16, 4, true><<<blocks, 128, smem, st>>>(in, filter, bias, out, g,
+                                                                           M, G, tpb);
     } else {
       LCE_DIRECT(0, 0, 0, 4);
     }
