@@ -163,6 +163,14 @@ def make_stage_inputs(batch, seed):
     return [rng.standard_normal((batch, hw, hw, c), dtype=np.float32) for (hw, c) in STAGES]
 
 
+def measured_bf16_peak():
+    try:
+        with open(os.path.join(REPO, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f).get("bf16_tflops"))
+    except Exception:
+        return None
+
+
 def ncu_traffic_per_launch(fname="r01_ncu_bconv_v8_summary.csv"):
     """Mean dram__bytes_read + dram__bytes_write per lce::bconv_kernel launch from the committed
     `ncu --set full` capture of this same command (profiles/r01_ncu_bconv_v8_summary.csv:
@@ -599,6 +607,7 @@ def main_b200(args):
     from compute_engine_b200 import capi
     capi.lib()
     hbm_peak, peak_src, sm_max = measured_peaks()
+    bf16_peak = measured_bf16_peak()
     popc_peak = 148 * 16 * sm_max * 1e6   # 15.98 POPC/clk/SM measured (profiles/r01_microbench_pipes.jsonl)
     if args.workload == "bgemm_sweep":
         rows = bgemm_sweep(args, D)
@@ -681,6 +690,9 @@ def main_b200(args):
                 "alg_bytes_per_launch": r["conv_bytes"] / n_launch,
                 "hbm": {"achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                         "frac": achieved / hbm_peak},
+                "vs_measured_bf16_dense": {"peak": bf16_peak, "unit": "TFLOP/s (MEASURED_PEAKS.json, tcgen05 "
+                                           "path; shown for scale only)",
+                                           "frac": (tops / bf16_peak) if bf16_peak else None},
                 "launches_timed": r["n_conv"],
                 "avg_launch_ms": r["conv_s_per_step"] * 1e3 / n_launch,
                 "share_of_step": r["conv_share"], "timing": r["timing_note"]}

@@ -296,6 +296,62 @@ __global__ void __launch_bounds__(256, 2) conv_gemm128_kernel(const float* __res
   }
 }
 
+// ---- plain GEMM for few output rows (FULLY_CONNECTED at batch 256: a 128 x 128 tiling would
+// give 16 CTAs to 148 SMs): 32 x 64 tiles, 2 x 4 outputs per thread, K chunks of 32 ----
+constexpr int kSM_ = 32, kSN_ = 64, kSK_ = 32;
+__global__ void __launch_bounds__(256) gemm_small_m_kernel(const float* __restrict__ A,
+                                                           const float* __restrict__ Wt,
+                                                           const float* __restrict__ bias,
+                                                           float* __restrict__ out, long long M,
+                                                           int N, int K, int act) {
+  __shared__ __align__(16) float A_s[kSK_][kSM_ + 2];
+  __shared__ __align__(16) float B_s[kSK_][kSN_ + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const long long m0 = static_cast<long long>(blockIdx.x) * kSM_;
+  const int n0 = blockIdx.y * kSN_;
+  const int arow = tid >> 3, akq = (tid & 7) * 4;      // A: 32 rows x 8 float4
+  const int bcol = tid >> 2, bkq = (tid & 3) * 8;      // B: 64 cols x 4 x 2 float4
+  float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+  for (int k0 = 0; k0 < K; k0 += kSK_) {
+    const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 a = (m0 + arow < M && k0 + akq < K)
+                         ? __ldg(reinterpret_cast<const float4*>(A + (m0 + arow) * K + k0 + akq)) : z;
+    float4 b[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      b[h] = (n0 + bcol < N && k0 + bkq + 4 * h < K)
+                 ? __ldg(reinterpret_cast<const float4*>(Wt + static_cast<size_t>(n0 + bcol) * K +
+                                                         k0 + bkq + 4 * h)) : z;
+    A_s[akq][arow] = a.x; A_s[akq + 1][arow] = a.y; A_s[akq + 2][arow] = a.z; A_s[akq + 3][arow] = a.w;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      B_s[bkq + 4 * h][bcol] = b[h].x; B_s[bkq + 4 * h + 1][bcol] = b[h].y;
+      B_s[bkq + 4 * h + 2][bcol] = b[h].z; B_s[bkq + 4 * h + 3][bcol] = b[h].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < kSK_; ++kk) {
+      const float2 av = *reinterpret_cast<const float2*>(&A_s[kk][ty * 2]);
+      const float4 bv = *reinterpret_cast<const float4*>(&B_s[kk][tx * 4]);
+      acc[0][0] = fmaf(av.x, bv.x, acc[0][0]); acc[0][1] = fmaf(av.x, bv.y, acc[0][1]);
+      acc[0][2] = fmaf(av.x, bv.z, acc[0][2]); acc[0][3] = fmaf(av.x, bv.w, acc[0][3]);
+      acc[1][0] = fmaf(av.y, bv.x, acc[1][0]); acc[1][1] = fmaf(av.y, bv.y, acc[1][1]);
+      acc[1][2] = fmaf(av.y, bv.z, acc[1][2]); acc[1][3] = fmaf(av.y, bv.w, acc[1][3]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const long long m = m0 + ty * 2 + i;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n < N) out[m * N + n] = apply_act(acc[i][j] + (bias ? bias[n] : 0.0f), act);
+    }
+  }
+}
+
 // ---- implicit-GEMM convolution, any filter / stride / dilation: 128 pixels x 64 channels x 16
 // tiles, 8 x 4 outputs per thread, register-prefetch double buffering. The k -> (tap, channel)
 // decomposition is tabulated once per CTA in shared memory (offset inside the image and the
@@ -418,6 +474,129 @@ __global__ void __launch_bounds__(256, 2) conv_igemm_kernel(const float* __restr
       *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
     else
       for (int q = 0; q < 4 && n + q < g.Cout; ++q) o[q] = v[q];
+  }
+}
+
+// Same tiling with 128 threads and 8 x 8 outputs per thread (rows {ty*4.., 64+ty*4..}, channels
+// {tx*4.., 32+tx*4..}): half the shared-memory reads per FMA of the 8 x 4 variant, whose ncu
+// profile on Bi-RealNet's stem showed the LSU / shared-memory pipe at 61-75 % next to 53 % FMA.
+__global__ void __launch_bounds__(128, 4) conv_igemm8x8_kernel(const float* __restrict__ in,
+                                                               const float* __restrict__ filter,
+                                                               const float* __restrict__ bias,
+                                                               float* __restrict__ out, ConvGeom g,
+                                                               long long M) {
+  __shared__ __align__(16) float A_s[2][kIK][kIM + 4];
+  __shared__ __align__(16) float B_s[2][kIK][kIN + 4];
+  extern __shared__ int ktab[];
+  const int K = g.KH * g.KW * g.Cin;
+  const int Kpad = (K + kIK - 1) / kIK * kIK;
+  int* koff = ktab;
+  int* kdydx = ktab + Kpad;
+  const int tid = threadIdx.x;
+  for (int k = tid; k < Kpad; k += 128) {
+    if (k < K) {
+      const int tap = k / g.Cin, ci = k - tap * g.Cin;
+      const int fy = tap / g.KW, fx = tap - fy * g.KW;
+      koff[k] = (fy * g.dh * g.W + fx * g.dw) * g.Cin + ci;
+      kdydx[k] = ((fy * g.dh) << 16) | (fx * g.dw);
+    } else {
+      koff[k] = 0;
+      kdydx[k] = 0x7fff7fff;
+    }
+  }
+  const long long m0 = static_cast<long long>(blockIdx.x) * kIM;
+  const int n0 = blockIdx.y * kIN;
+  // loader roles: A -- row tid, all 16 k of the chunk; B -- channel tid >> 1, 8 consecutive k
+  const int lrow = tid;
+  const int bn = tid >> 1, bkq = (tid & 1) * 8;
+  int iy0 = 0, ix0 = 0;
+  const float* base = in;
+  const bool row_ok = m0 + lrow < M;
+  if (row_ok) {
+    const long long m = m0 + lrow;
+    const int ohw = g.OH * g.OW;
+    const long long b = m / ohw;
+    const int r = static_cast<int>(m - b * ohw);
+    const int oy = r / g.OW, ox = r - oy * g.OW;
+    iy0 = oy * g.sh - g.ph;
+    ix0 = ox * g.sw - g.pw;
+    base = in + ((b * g.H + iy0) * g.W + ix0) * g.Cin;
+  }
+  const bool bn_ok = n0 + bn < g.Cout;
+  const float* wrow = filter + static_cast<size_t>(bn_ok ? n0 + bn : 0) * K;
+  __syncthreads();
+
+  float ra[16], rb[8];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) {
+      const int k = k0 + e;
+      const int d = kdydx[k];
+      const int iy = iy0 + (d >> 16), ix = ix0 + (d & 0xffff);
+      const bool ok = row_ok && static_cast<unsigned>(iy) < static_cast<unsigned>(g.H) &&
+                      static_cast<unsigned>(ix) < static_cast<unsigned>(g.W);
+      ra[e] = ok ? __ldg(base + koff[k]) : 0.0f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      const int k = k0 + bkq + e;
+      rb[e] = (bn_ok && k < K) ? __ldg(wrow + k) : 0.0f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int e = 0; e < 16; ++e) A_s[buf][e][lrow] = ra[e];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) B_s[buf][bkq + e][bn] = rb[e];
+  };
+  const int tx = tid & 7, ty = tid >> 3;
+  float acc[8][8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) acc[i][j] = 0.0f;
+  fetch(0);
+  stash(0);
+  __syncthreads();
+  const int nk = Kpad / kIK;
+  for (int it = 0; it < nk; ++it) {
+    const int buf = it & 1;
+    if (it + 1 < nk) fetch((it + 1) * kIK);
+#pragma unroll
+    for (int kk = 0; kk < kIK; ++kk) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&A_s[buf][kk][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&A_s[buf][kk][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&B_s[buf][kk][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&B_s[buf][kk][32 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    if (it + 1 < nk) {
+      stash(buf ^ 1);
+      __syncthreads();
+    }
+  }
+  const bool vec = (g.Cout & 3) == 0 && !(reinterpret_cast<uintptr_t>(out) & 15);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+    if (m >= M) continue;
+#pragma unroll
+    for (int jh = 0; jh < 2; ++jh) {
+      const int n = n0 + jh * 32 + tx * 4;
+      float v[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+        v[q] = apply_act(acc[i][jh * 4 + q] + ((bias && n + q < g.Cout) ? bias[n + q] : 0.0f), g.act);
+      float* o = out + m * g.Cout + n;
+      if (vec && n + 3 < g.Cout) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+      else
+        for (int q = 0; q < 4 && n + q < g.Cout; ++q) o[q] = v[q];
+    }
   }
 }
 
@@ -897,6 +1076,12 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   }
   const bool plain = g.KH == 1 && g.KW == 1 && g.sh == 1 && g.sw == 1 && (K & 3) == 0 &&
                      !((uintptr_t)in & 15) && !((uintptr_t)filter & 15) && !((uintptr_t)out & 15);
+  if (plain && ((M + kPM - 1) / kPM) * ((g.Cout + kPN - 1) / kPN) < 74) {
+    dim3 sgrid(static_cast<unsigned>((M + kSM_ - 1) / kSM_), (g.Cout + kSN_ - 1) / kSN_);
+    gemm_small_m_kernel<<<sgrid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, M, g.Cout, K,
+                                                              g.act);
+    return launch_check("gemm_small_m_kernel");
+  }
   if (plain) {
     dim3 grid(static_cast<unsigned>((M + kPM - 1) / kPM), (g.Cout + kPN - 1) / kPN);
     conv_gemm128_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, M, g.Cout, K,
@@ -906,8 +1091,16 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   if (K <= kIKMax && static_cast<long long>(g.H) * g.W * g.Cin < (1LL << 31)) {
     dim3 igrid(static_cast<unsigned>((M + kIM - 1) / kIM), (g.Cout + kIN - 1) / kIN);
     const size_t ksmem = static_cast<size_t>((K + kIK - 1) / kIK * kIK) * 2 * sizeof(int);
-    conv_igemm_kernel<<<igrid, 256, ksmem, as_stream(stream)>>>(in, filter, bias, out, g, M);
-    return launch_check("conv_igemm_kernel");
+    static const bool use8x4 = [] {
+      const char* e = getenv("LCE_B200_IGEMM_8X4");
+      return e && e[0] == '1';
+    }();
+    if (use8x4) {
+      conv_igemm_kernel<<<igrid, 256, ksmem, as_stream(stream)>>>(in, filter, bias, out, g, M);
+      return launch_check("conv_igemm_kernel");
+    }
+    conv_igemm8x8_kernel<<<igrid, 128, ksmem, as_stream(stream)>>>(in, filter, bias, out, g, M);
+    return launch_check("conv_igemm8x8_kernel");
   }
   dim3 grid(static_cast<unsigned>((M + kGM - 1) / kGM), (g.Cout + kGN - 1) / kGN);
   conv_gemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, M);
