@@ -225,6 +225,68 @@ TfLiteStatus PoolDwInvoke(TfLiteContext* c, TfLiteNode* n) {
   return kTfLiteOk;
 }
 
+// ---- fused stem CONV_2D(3x3 s2 -> 16) + DEPTHWISE_CONV_2D(3x3 s2) + CONV_2D(1x1 -> 64) ---- //
+// Created by Graph::FuseFloatGlue; builtin_data = { conv1, depthwise, pointwise } BuiltinParams;
+// inputs [x, w1, b1, w2, b2, w3, b3].
+struct StemParams {
+  BuiltinParams c1, dw, pw;
+};
+void* StemInit(TfLiteContext*, const char* buffer, size_t length) {
+  auto* p = new StemParams();
+  memset(p, 0, sizeof(*p));
+  if (buffer && length >= sizeof(StemParams)) memcpy(p, buffer, sizeof(StemParams));
+  return p;
+}
+void StemFree(TfLiteContext*, void* p) { delete static_cast<StemParams*>(p); }
+void FillConvDesc(lce_f32_conv_desc* d, const BuiltinParams& bp, int batch, int h, int w, int cin,
+                  const TfLiteTensor* filter) {
+  d->batch = batch; d->in_h = h; d->in_w = w; d->in_c = cin;
+  d->filter_h = filter->dims->data[1]; d->filter_w = filter->dims->data[2];
+  d->stride_h = bp.stride_h; d->stride_w = bp.stride_w;
+  d->dilation_h = bp.dilation_h; d->dilation_w = bp.dilation_w;
+  d->padding = bp.padding; d->activation = bp.activation;
+}
+bool StemDescs(TfLiteContext* c, TfLiteNode* n, lce_f32_conv_desc* d1, lce_f32_conv_desc* d2,
+               lce_f32_conv_desc* d3) {
+  const auto& sp = *static_cast<StemParams*>(n->user_data);
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const TfLiteTensor* w1 = T(c, n->inputs, 1);
+  const TfLiteTensor* w2 = T(c, n->inputs, 3);
+  const TfLiteTensor* w3 = T(c, n->inputs, 5);
+  if (!in || !w1 || !w2 || !w3 || in->dims->size != 4 || w1->dims->size != 4 ||
+      w2->dims->size != 4 || w3->dims->size != 4)
+    return false;
+  int oh, ow;
+  FillConvDesc(d1, sp.c1, in->dims->data[0], in->dims->data[1], in->dims->data[2],
+               in->dims->data[3], w1);
+  d1->out_c = w1->dims->data[0];
+  if (lce_b200_f32_conv_out_shape(d1, &oh, &ow)) return false;
+  FillConvDesc(d2, sp.dw, d1->batch, oh, ow, d1->out_c, w2);
+  d2->out_c = w2->dims->data[3];
+  if (lce_b200_f32_conv_out_shape(d2, &oh, &ow)) return false;
+  FillConvDesc(d3, sp.pw, d1->batch, oh, ow, d2->out_c, w3);
+  d3->out_c = w3->dims->data[0];
+  return true;
+}
+TfLiteStatus StemPrepare(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_conv_desc d1, d2, d3;
+  B_ENSURE(c, StemDescs(c, n, &d1, &d2, &d3), "fused stem: bad shapes");
+  int oh, ow;
+  B_CAPI(c, lce_b200_f32_conv_out_shape(&d3, &oh, &ow));
+  return Resize(c, T(c, n->outputs, 0), {d3.batch, oh, ow, d3.out_c});
+}
+TfLiteStatus StemInvoke(TfLiteContext* c, TfLiteNode* n) {
+  lce_f32_conv_desc d1, d2, d3;
+  StemDescs(c, n, &d1, &d2, &d3);
+  auto f = [&](int i) -> const float* {
+    const TfLiteTensor* t = T(c, n->inputs, i);
+    return t ? t->data.f : nullptr;
+  };
+  B_CAPI(c, lce_b200_f32_stem_conv_dw_pw(&d1, &d2, &d3, f(0), f(1), f(2), f(3), f(4), f(5), f(6),
+                                         T(c, n->outputs, 0)->data.f, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
 // ------------------------------ ADD / MUL / RELU ------------------------------ //
 TfLiteStatus EltPrepare(TfLiteContext* c, TfLiteNode* n) {
   const TfLiteTensor* a = T(c, n->inputs, 0);
@@ -428,6 +490,10 @@ TfLiteStatus ConcatInvoke(TfLiteContext* c, TfLiteNode* n) {
 
 }  // namespace
 
+const TfLiteRegistration* FusedStemRegistration() {
+  static TfLiteRegistration r = {StemInit, StemFree, StemPrepare, StemInvoke};
+  return &r;
+}
 const TfLiteRegistration* FusedPoolDepthwiseRegistration() {
   static TfLiteRegistration r = {PoolDwInit, PoolDwFree, PoolDwPrepare, PoolDwInvoke};
   return &r;

@@ -381,10 +381,91 @@ int Graph::FuseResidualBlocks() {
 }
 
 const TfLiteRegistration* FusedPoolDepthwiseRegistration();  // builtin_ops.cc
+const TfLiteRegistration* FusedStemRegistration();
+
+// CONV_2D(3x3, stride 2, C_in <= 4 -> 16) -> DEPTHWISE_CONV_2D(3x3, stride 2, multiplier 1) ->
+// CONV_2D(1x1, stride 1, 16 -> 64), each intermediate consumed once: one node (QuickNet's stem).
+int Graph::FuseStem() {
+  auto sole_consumer = [&](int t, size_t after) -> size_t {
+    if (std::find(outputs_.begin(), outputs_.end(), t) != outputs_.end()) return nodes_.size();
+    size_t found = nodes_.size();
+    int n = 0;
+    for (size_t k = 0; k < nodes_.size(); ++k)
+      for (int q = 0; q < nodes_[k]->node.inputs->size; ++q)
+        if (nodes_[k]->node.inputs->data[q] == t) { ++n; found = k; }
+    return (n == 1 && found > after && nodes_[found]->node.inputs->data[0] == t) ? found
+                                                                                 : nodes_.size();
+  };
+  auto bp = [](const NodeRecord& r) {
+    return reinterpret_cast<const BuiltinParams*>(r.builtin_blob.data());
+  };
+  auto dims4 = [&](int t, int d) { return tensors_[t].dims->size == 4 ? tensors_[t].dims->data[d] : -1; };
+  for (size_t i = 0; i < nodes_.size(); ++i) {
+    NodeRecord& c1 = *nodes_[i];
+    if (c1.name != "builtin:3" || c1.initialized || c1.node.inputs->size < 3 ||
+        c1.builtin_blob.size() < sizeof(BuiltinParams))
+      continue;
+    const int w1 = c1.node.inputs->data[1];
+    if (dims4(w1, 0) != 16 || dims4(w1, 1) != 3 || dims4(w1, 2) != 3 || dims4(w1, 3) > 4 ||
+        bp(c1)->stride_h != 2 || bp(c1)->stride_w != 2 || bp(c1)->dilation_h != 1 ||
+        bp(c1)->dilation_w != 1 || tensors_[c1.node.outputs->data[0]].type != kTfLiteFloat32)
+      continue;
+    const size_t di = sole_consumer(c1.node.outputs->data[0], i);
+    if (di >= nodes_.size()) continue;
+    NodeRecord& dw = *nodes_[di];
+    if (dw.name != "builtin:4" || dw.initialized || dw.node.inputs->size < 3 ||
+        dw.builtin_blob.size() < sizeof(BuiltinParams))
+      continue;
+    const int w2 = dw.node.inputs->data[1];
+    if (dims4(w2, 1) != 3 || dims4(w2, 2) != 3 || dims4(w2, 3) != 16 || bp(dw)->stride_h != 2 ||
+        bp(dw)->stride_w != 2 || bp(dw)->dilation_h != 1 || bp(dw)->dilation_w != 1 ||
+        bp(dw)->depth_multiplier != 1)
+      continue;
+    const size_t pi = sole_consumer(dw.node.outputs->data[0], di);
+    if (pi >= nodes_.size()) continue;
+    NodeRecord& pw = *nodes_[pi];
+    if (pw.name != "builtin:3" || pw.initialized || pw.node.inputs->size < 3 ||
+        pw.builtin_blob.size() < sizeof(BuiltinParams))
+      continue;
+    const int w3 = pw.node.inputs->data[1];
+    if (dims4(w3, 0) != 64 || dims4(w3, 1) != 1 || dims4(w3, 2) != 1 || dims4(w3, 3) != 16 ||
+        bp(pw)->stride_h != 1 || bp(pw)->stride_w != 1)
+      continue;
+    std::vector<uint8_t> blob(3 * sizeof(BuiltinParams));
+    memcpy(blob.data(), bp(c1), sizeof(BuiltinParams));
+    memcpy(blob.data() + sizeof(BuiltinParams), bp(dw), sizeof(BuiltinParams));
+    memcpy(blob.data() + 2 * sizeof(BuiltinParams), bp(pw), sizeof(BuiltinParams));
+    std::vector<int> ins{c1.node.inputs->data[0], w1, c1.node.inputs->data[2],
+                         w2, dw.node.inputs->data[2], w3, pw.node.inputs->data[2]};
+    std::vector<int> outs{pw.node.outputs->data[0]};
+    LceB200IntArrayFree(c1.node.inputs);
+    LceB200IntArrayFree(c1.node.outputs);
+    c1.node.inputs = MakeDims(ins);
+    c1.node.outputs = MakeDims(outs);
+    c1.builtin_blob = blob;
+    c1.node.builtin_data = c1.builtin_blob.data();
+    c1.registration = FusedStemRegistration();
+    c1.name = "CONV_2D+DEPTHWISE_CONV_2D+CONV_2D";
+    for (size_t victim : {pi, di}) {   // erase the later node first
+      NodeRecord& v = *nodes_[victim];
+      LceB200IntArrayFree(v.node.inputs);
+      LceB200IntArrayFree(v.node.outputs);
+      LceB200IntArrayFree(v.node.temporaries);
+      LceB200IntArrayFree(v.node.intermediates);
+      nodes_.erase(nodes_.begin() + victim);
+    }
+    allocated_ = false;
+    return 2;
+  }
+  return 0;
+}
 
 int Graph::FuseFloatGlue() {
   if (!device_arena_) return 0;
-  int removed = 0;
+  // the one-pass stem is correct (bit-identical) but not yet faster than its three kernels
+  // (same instruction count, they are not memory bound): opt-in until it is
+  const char* stem_env = getenv("LCE_B200_FUSE_STEM");
+  int removed = (stem_env && stem_env[0] == '1') ? FuseStem() : 0;
   for (size_t i = 0; i < nodes_.size(); ++i) {
     NodeRecord& pool = *nodes_[i];
     if (pool.name != "builtin:17" || pool.initialized ||

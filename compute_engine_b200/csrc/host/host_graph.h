@@ -75,8 +75,10 @@ class Graph {
 
   // Fusions among the float builtins around the binary path:
   //   MAX_POOL_2D(2x2, stride 1, VALID) -> DEPTHWISE_CONV_2D(3x3)  =>  one node
+  //   CONV_2D(3x3 s2 -> 16) -> DEPTHWISE_CONV_2D(3x3 s2) -> CONV_2D(1x1 -> 64)  =>  one node
   // (QuickNet's anti-aliased down-sampling). Bit-identical. Returns the nodes removed.
   int FuseFloatGlue();
+  int FuseStem();  // part of FuseFloatGlue: stem conv + depthwise + pointwise conv -> one node
 
   // init (first time) + prepare of every node in order, then arena allocation.
   TfLiteStatus AllocateTensors();

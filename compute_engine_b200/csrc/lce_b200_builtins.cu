@@ -976,6 +976,188 @@ __global__ void __launch_bounds__(256) pad4d32_kernel(const uint32_t* __restrict
   out[i] = v;
 }
 
+// ---- fused stem: CONV_2D(3x3, stride 2, Cin <= 4 -> 16) -> DEPTHWISE_CONV_2D(3x3, stride 2)
+//      -> CONV_2D(1x1, 16 -> 64) in one pass (QuickNet's stem). One CTA = an 8 x 8 tile of the final
+// map of one image: the 35 x 35 input patch, the 17 x 17 x 16 first-conv tile and the 8 x 8 x 16
+// depthwise tile live in shared memory; the 205 MB + 51 MB intermediates never reach HBM. Every
+// output is accumulated in the same order as conv_direct16_kernel / depthwise_v4_kernel, so the
+// result is bit-identical to the three-kernel sequence.
+constexpr int kStT = 8, kStC1 = 16, kStC2 = 64;
+constexpr int kStR1 = 2 * kStT + 1;          // 17 first-conv rows / cols per tile
+constexpr int kStR0 = 2 * (kStR1 - 1) + 3;   // 35 input rows / cols per tile
+constexpr int kStPitch = kStC1 + 4;          // 20 floats: 16-byte aligned, conflict-free rows
+struct StemGeom {
+  int B, H, W, Cin, OH1, OW1, ph1, pw1, OH2, OW2, ph2, pw2, act1, act2, act3;
+};
+constexpr int kStemSmemFloats = kStR0 * kStR0 * 4 + kStR1 * kStR1 * kStPitch + kStT * kStT * kStPitch +
+                                36 * kStC1 + 9 * kStC1 + kStC1 * kStC2 + kStC1 + kStC1 + kStC2;
+__global__ void __launch_bounds__(256) stem_fused_kernel(const float* __restrict__ in,
+                                                         const float* __restrict__ w1,
+                                                         const float* __restrict__ b1,
+                                                         const float* __restrict__ w2,
+                                                         const float* __restrict__ b2,
+                                                         const float* __restrict__ w3,
+                                                         const float* __restrict__ b3,
+                                                         float* __restrict__ out, StemGeom s) {
+  extern __shared__ __align__(16) float sm[];
+  float* patch = sm;                                         // [35][35][Cin]
+  float* c1 = patch + kStR0 * kStR0 * 4;                     // [17*17][20]
+  float* dws = c1 + kStR1 * kStR1 * kStPitch;                // [64][20]
+  float* w1s = dws + kStT * kStT * kStPitch;                 // [9*Cin][16]
+  float* w2s = w1s + 36 * kStC1;                             // [9][16]
+  float* w3s = w2s + 9 * kStC1;                              // [16][64]
+  float* b1s = w3s + kStC1 * kStC2;
+  float* b2s = b1s + kStC1;
+  float* b3s = b2s + kStC1;
+  const int tid = threadIdx.x;
+  const int Cin = s.Cin, K1 = 9 * Cin;
+  const long long b = blockIdx.z;
+  const int oy2_0 = blockIdx.y * kStT, ox2_0 = blockIdx.x * kStT;
+  const int y1_0 = oy2_0 * 2 - s.ph2, x1_0 = ox2_0 * 2 - s.pw2;   // first-conv coords of the tile
+  const int y0_0 = y1_0 * 2 - s.ph1, x0_0 = x1_0 * 2 - s.pw1;     // input coords of the patch
+
+  // weights: w1 [16][3][3][Cin] -> [k][16]; w2 [1][3][3][16]; w3 [64][16] -> [k][64]
+  for (int i = tid; i < K1 * kStC1; i += 256) {
+    const int c = i & 15, k = i >> 4;
+    w1s[k * kStC1 + c] = w1[c * K1 + k];
+  }
+  for (int i = tid; i < 9 * kStC1; i += 256) w2s[i] = w2[i];
+  for (int i = tid; i < kStC1 * kStC2; i += 256) {
+    const int c = i & 63, k = i >> 6;
+    w3s[k * kStC2 + c] = w3[c * kStC1 + k];
+  }
+  if (tid < kStC1) {
+    b1s[tid] = b1 ? b1[tid] : 0.0f;
+    b2s[tid] = b2 ? b2[tid] : 0.0f;
+  }
+  if (tid < kStC2) b3s[tid] = b3 ? b3[tid] : 0.0f;
+  // input patch, zero outside the image (the first conv's SAME padding)
+  const float* img = in + b * s.H * s.W * Cin;
+  for (int i = tid; i < kStR0 * kStR0; i += 256) {
+    const int r = i / kStR0, col = i - r * kStR0;
+    const int gy = y0_0 + r, gx = x0_0 + col;
+    const bool ok = static_cast<unsigned>(gy) < static_cast<unsigned>(s.H) &&
+                    static_cast<unsigned>(gx) < static_cast<unsigned>(s.W);
+    const float* src = img + (static_cast<long long>(gy) * s.W + gx) * Cin;
+    for (int ci = 0; ci < Cin; ++ci) patch[i * Cin + ci] = ok ? __ldg(src + ci) : 0.0f;
+  }
+  __syncthreads();
+
+  // first conv: task = (two horizontally adjacent tile pixels, all 16 channels) -- 32 FMAs per
+  // 2 scalar + 4 vector shared-memory reads, the density of conv_direct16_kernel
+  constexpr int kPairs = (kStR1 + 1) / 2;   // 9 pixel pairs per tile row (the last one half empty)
+  for (int id = tid; id < kStR1 * kPairs; id += 256) {
+    const int py = id / kPairs, pp = id - py * kPairs;
+    const int px = pp * 2;
+    float acc[2][16];
+#pragma unroll
+    for (int p = 0; p < 2; ++p)
+#pragma unroll
+      for (int c = 0; c < 16; ++c) acc[p][c] = 0.0f;
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy)
+#pragma unroll
+      for (int fx = 0; fx < 3; ++fx) {
+        // the second pixel of the last pair reads 2 columns past the patch: clamp (never stored)
+        const int col0 = 2 * px + fx;
+        const int col1 = min(col0 + 2, kStR0 - 1);
+        const float* xp0 = patch + ((2 * py + fy) * kStR0 + col0) * Cin;
+        const float* xp1 = patch + ((2 * py + fy) * kStR0 + col1) * Cin;
+        const float* wp = w1s + (fy * 3 + fx) * Cin * kStC1;
+        for (int ci = 0; ci < Cin; ++ci) {
+          const float x0 = xp0[ci], x1 = xp1[ci];
+          const float4* w4 = reinterpret_cast<const float4*>(wp + ci * kStC1);
+#pragma unroll
+          for (int qq = 0; qq < 4; ++qq) {
+            const float4 w = w4[qq];
+            acc[0][4 * qq] = fmaf(x0, w.x, acc[0][4 * qq]);
+            acc[0][4 * qq + 1] = fmaf(x0, w.y, acc[0][4 * qq + 1]);
+            acc[0][4 * qq + 2] = fmaf(x0, w.z, acc[0][4 * qq + 2]);
+            acc[0][4 * qq + 3] = fmaf(x0, w.w, acc[0][4 * qq + 3]);
+            acc[1][4 * qq] = fmaf(x1, w.x, acc[1][4 * qq]);
+            acc[1][4 * qq + 1] = fmaf(x1, w.y, acc[1][4 * qq + 1]);
+            acc[1][4 * qq + 2] = fmaf(x1, w.z, acc[1][4 * qq + 2]);
+            acc[1][4 * qq + 3] = fmaf(x1, w.w, acc[1][4 * qq + 3]);
+          }
+        }
+      }
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+      if (px + p >= kStR1) continue;
+      const int y1 = y1_0 + py, x1 = x1_0 + px + p;
+      const bool inmap = static_cast<unsigned>(y1) < static_cast<unsigned>(s.OH1) &&
+                         static_cast<unsigned>(x1) < static_cast<unsigned>(s.OW1);
+      float4* dst = reinterpret_cast<float4*>(c1 + (py * kStR1 + px + p) * kStPitch);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        dst[qq] = inmap ? make_float4(apply_act(acc[p][4 * qq] + b1s[4 * qq], s.act1),
+                                      apply_act(acc[p][4 * qq + 1] + b1s[4 * qq + 1], s.act1),
+                                      apply_act(acc[p][4 * qq + 2] + b1s[4 * qq + 2], s.act1),
+                                      apply_act(acc[p][4 * qq + 3] + b1s[4 * qq + 3], s.act1))
+                        : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  }
+  __syncthreads();
+
+  {  // depthwise 3x3 stride 2: thread = (tile pixel, 4-channel group); out-of-range taps skipped
+    const int p2 = tid >> 2, q = tid & 3;
+    const int ly = p2 >> 3, lx = p2 & 7;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int fy = 0; fy < 3; ++fy) {
+      const int y1 = y1_0 + 2 * ly + fy;
+      if (static_cast<unsigned>(y1) >= static_cast<unsigned>(s.OH1)) continue;
+#pragma unroll
+      for (int fx = 0; fx < 3; ++fx) {
+        const int x1 = x1_0 + 2 * lx + fx;
+        if (static_cast<unsigned>(x1) >= static_cast<unsigned>(s.OW1)) continue;
+        const float4 x = *reinterpret_cast<const float4*>(
+            c1 + ((2 * ly + fy) * kStR1 + 2 * lx + fx) * kStPitch + q * 4);
+        const float4 w = *reinterpret_cast<const float4*>(w2s + (fy * 3 + fx) * kStC1 + q * 4);
+        acc.x = fmaf(x.x, w.x, acc.x); acc.y = fmaf(x.y, w.y, acc.y);
+        acc.z = fmaf(x.z, w.z, acc.z); acc.w = fmaf(x.w, w.w, acc.w);
+      }
+    }
+    const float4 bb = *reinterpret_cast<const float4*>(b2s + q * 4);
+    *reinterpret_cast<float4*>(dws + p2 * kStPitch + q * 4) =
+        make_float4(apply_act(acc.x + bb.x, s.act2), apply_act(acc.y + bb.y, s.act2),
+                    apply_act(acc.z + bb.z, s.act2), apply_act(acc.w + bb.w, s.act2));
+  }
+  __syncthreads();
+
+  {  // pointwise 16 -> 64: thread = (tile pixel, 16-channel group)
+    const int p2 = tid >> 2, grp = tid & 3;
+    const int oy2 = oy2_0 + (p2 >> 3), ox2 = ox2_0 + (p2 & 7);
+    float acc[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) acc[c] = 0.0f;
+    const float* xp = dws + p2 * kStPitch;
+#pragma unroll
+    for (int k = 0; k < kStC1; ++k) {
+      const float x = xp[k];
+      const float4* w4 = reinterpret_cast<const float4*>(w3s + k * kStC2 + grp * 16);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const float4 w = w4[qq];
+        acc[4 * qq] = fmaf(x, w.x, acc[4 * qq]);
+        acc[4 * qq + 1] = fmaf(x, w.y, acc[4 * qq + 1]);
+        acc[4 * qq + 2] = fmaf(x, w.z, acc[4 * qq + 2]);
+        acc[4 * qq + 3] = fmaf(x, w.w, acc[4 * qq + 3]);
+      }
+    }
+    if (oy2 < s.OH2 && ox2 < s.OW2) {
+      const float* bb = b3s + grp * 16;
+      float4* o = reinterpret_cast<float4*>(out + ((b * s.OH2 + oy2) * s.OW2 + ox2) * kStC2 + grp * 16);
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq)
+        o[qq] = make_float4(apply_act(acc[4 * qq] + bb[4 * qq], s.act3),
+                            apply_act(acc[4 * qq + 1] + bb[4 * qq + 1], s.act3),
+                            apply_act(acc[4 * qq + 2] + bb[4 * qq + 2], s.act3),
+                            apply_act(acc[4 * qq + 3] + bb[4 * qq + 3], s.act3));
+    }
+  }
+}
+
 int make_geom(const lce_f32_conv_desc* d, ConvGeom* g) {
   if (d->batch < 0 || d->in_h < 1 || d->in_w < 1 || d->in_c < 1 || d->out_c < 1 ||
       d->filter_h < 1 || d->filter_w < 1 || d->stride_h < 1 || d->stride_w < 1 ||
@@ -1215,6 +1397,37 @@ int lce_b200_f32_maxpool2x2_depthwise3x3(const lce_f32_pool_desc* pool, const lc
       reinterpret_cast<const float4*>(bias), reinterpret_cast<float4*>(out), pool->in_h,
       pool->in_w, C4, ph_, pw_, g.OH, g.OW, g.sh, g.sw, g.ph, g.pw, g.act);
   return launch_check("pool2_dw3_v4_kernel");
+}
+
+int lce_b200_f32_stem_conv_dw_pw(const lce_f32_conv_desc* conv1, const lce_f32_conv_desc* dw,
+                                 const lce_f32_conv_desc* pw, const float* in, const float* w1,
+                                 const float* b1, const float* w2, const float* b2,
+                                 const float* w3, const float* b3, float* out, void* stream) {
+  ConvGeom g1, g2, g3;
+  if (make_geom(conv1, &g1) || make_geom(dw, &g2) || make_geom(pw, &g3)) return 1;
+  const bool ok =
+      g1.KH == 3 && g1.KW == 3 && g1.sh == 2 && g1.sw == 2 && g1.dh == 1 && g1.dw == 1 &&
+      g1.Cin >= 1 && g1.Cin <= 4 && g1.Cout == kStC1 &&
+      g2.KH == 3 && g2.KW == 3 && g2.sh == 2 && g2.sw == 2 && g2.dh == 1 && g2.dw == 1 &&
+      g2.Cin == kStC1 && g2.Cout == kStC1 && g2.H == g1.OH && g2.W == g1.OW && g2.B == g1.B &&
+      g3.KH == 1 && g3.KW == 1 && g3.sh == 1 && g3.sw == 1 && g3.Cin == kStC1 &&
+      g3.Cout == kStC2 && g3.H == g2.OH && g3.W == g2.OW && g3.B == g1.B;
+  if (!ok) return fail("stem_conv_dw_pw: unsupported shapes (3x3/s2 -> 16, depthwise 3x3/s2, 1x1 -> 64)");
+  if (((uintptr_t)out & 15) || g1.B > 65535) return fail("stem_conv_dw_pw: unaligned output or batch too large");
+  if (g1.B == 0 || g2.OH == 0 || g2.OW == 0) return 0;
+  StemGeom s{g1.B, g1.H, g1.W, g1.Cin, g1.OH, g1.OW, g1.ph, g1.pw, g2.OH, g2.OW, g2.ph, g2.pw,
+             g1.act, g2.act, g3.act};
+  static bool attr = false;
+  const size_t smem = kStemSmemFloats * sizeof(float);
+  if (!attr) {
+    if (cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(smem)) != cudaSuccess)
+      return fail("stem_conv_dw_pw: cannot raise the shared-memory limit");
+    attr = true;
+  }
+  dim3 grid((g2.OW + kStT - 1) / kStT, (g2.OH + kStT - 1) / kStT, g1.B);
+  stem_fused_kernel<<<grid, 256, smem, as_stream(stream)>>>(in, w1, b1, w2, b2, w3, b3, out, s);
+  return launch_check("stem_fused_kernel");
 }
 
 int lce_b200_f32_add(const float* a, const float* b, float* out, int64_t n, int64_t b_len,

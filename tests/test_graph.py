@@ -206,20 +206,33 @@ def test_residual_block_fusion_rewrites_the_graph():
     names = [g.node_name(i) for i in range(g.num_nodes())]
     assert names.count("MAX_POOL_2D+DEPTHWISE_CONV_2D") == 3 and "builtin:17" not in names
     assert names.count("builtin:4") == 1               # the stem's depthwise stays
+    assert g.fuse_float_glue() == 0                    # idempotent
+    g.close()
+
+
+def test_stem_fusion_is_opt_in(monkeypatch):
+    """LCE_B200_FUSE_STEM=1: conv 3x3 s2 -> depthwise 3x3 s2 -> conv 1x1 of the stem as one node."""
+    monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")
+    g = H.HostGraph.from_tflite(zoo.quicknet(batch=1, image=64, seed=3), device_arena=True)
+    assert g.fuse_all() == 28 + 5 and g.num_nodes() == 31
+    names = [g.node_name(i) for i in range(g.num_nodes())]
+    assert names[0] == "CONV_2D+DEPTHWISE_CONV_2D+CONV_2D" and "builtin:4" not in names
+    assert names.count("builtin:3") == 3               # the transitions' 1x1 convs
     g.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("family", ["quicknet", "birealnet18"])
-def test_gpu_fused_graph_is_bit_identical_to_unfused(family):
-    blob = zoo.MODELS[family](batch=1, image=64, seed=11)
-    x = np.random.default_rng(4).standard_normal((5, 64, 64, 3)).astype(np.float32)
+@pytest.mark.parametrize("family,image", [("quicknet", 64), ("quicknet", 88), ("birealnet18", 64)])
+def test_gpu_fused_graph_is_bit_identical_to_unfused(family, image, monkeypatch):
+    monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")       # include the opt-in stem fusion
+    blob = zoo.MODELS[family](batch=1, image=image, seed=11)
+    x = np.random.default_rng(4).standard_normal((5, image, image, 3)).astype(np.float32)
     outs = []
     for fuse in (False, True):
         g = H.HostGraph.from_tflite(blob, device_arena=True)
         if fuse:
             assert g.fuse_residual_blocks() > 0
-            assert g.fuse_float_glue() == (3 if family == "quicknet" else 0)
+            assert g.fuse_float_glue() == (5 if family == "quicknet" else 0)
         g.resize_input(g.inputs()[0], x.shape)
         g.allocate_tensors()
         g.enable_cuda_graph(True)
