@@ -5,7 +5,9 @@
   python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 One "step" = one pass of the workload over one batch of synthetic input; rank 0 prints
-ONE JSON line. Every field is explained in DESIGN.md section 6.
+ONE JSON line. Every field is explained in DESIGN.md section 6. At N = 1 the graph workloads
+are measured twice in the same run: with the default kernel selection (`value`, `roofline`)
+and with every LceBconv2d on the XOR + POPC kernel (`xor_popc_path`, LCE_B200_BCONV_IMMA=0).
 
 Workloads (config.workload):
   quicknet         (default; BASELINE.json configs[1]) the full QuickNet `.tflite` graph,

@@ -120,7 +120,7 @@ struct GemmCore {
   int32_t* thr = nullptr;
   int32_t* tap_popc = nullptr;  // zero-padding correction table
   size_t smem_bytes = 0;
-  // experimental int8-tensor-pipe inner product (lce_b200_imma.cuh), LCE_B200_BCONV_IMMA=1
+  // int8 tensor-pipe inner product (lce_b200_imma.cuh); absent when LCE_B200_BCONV_IMMA=0 or ineligible
   int32_t* wt_nat = nullptr;    // weights expanded to int8 mma B fragments (8x the packed bytes)
   int32_t* wpop = nullptr;      // popcount of each channel's filter row (padded by BN)
   int imma_Kc_v = 0, imma_chunks = 1;
@@ -198,7 +198,7 @@ int launch_conv(const GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
   if (m_tiles > INT_MAX) return fail("too many output pixels");
   if (p.img_words >= (1LL << 31)) return fail("input image too large (>= 2^31 packed words)");
   if (c.wt_nat != nullptr && p.vec_store) {
-    // experimental int8 tensor-pipe inner product: 128 x 64 tiles, same integer results
+    // int8 tensor-pipe inner product: 128 x 64 tiles, the same int32 accumulators as bconv_kernel
     lce::ConvKParams q = p;
     q.wt = c.wt_nat; q.wpop = c.wpop;
     q.Kc_v = c.imma_Kc_v; q.n_chunks = c.imma_chunks;

@@ -233,7 +233,7 @@ __device__ __forceinline__ int round_saturate_i8(float y) {
 // ------------------------------------------------------------------------- //
 // K2/K3: binary implicit-GEMM convolution (a plain BGEMM is the 1x1 case).
 //   acc[m][n] = sum_k popc(A[m][k] ^ W[n][k]),  k = (tap, channel word)
-// One CTA computes a 128-pixel x 64-channel tile; K is staged chunk by chunk:
+// One CTA computes a 64-pixel x 64-channel tile; K is staged chunk by chunk:
 // weights by one bulk TMA copy from the pre-tiled layout, activation patches by
 // zero-filling 4V-byte cp.async (out-of-bounds taps read as 0 bits = +1, the
 // reference's one-padding: reference.h:106, optimized_bgemm.h:30-31).
@@ -486,7 +486,7 @@ __device__ __forceinline__ void epilogue_raw_fast(const ConvKParams& p, int (&ac
 
 // Position j*8+tn of the weight tile holds channel tn*8+j, so each thread owns 8 CONSECUTIVE
 // output channels and stores them with 128-bit writes. mulp / biasp / thrp point at this
-// thread's first channel (global memory, or the persistent kernel's shared-memory copy).
+// thread's first channel.
 template <int OUT>
 __device__ __forceinline__ void epilogue_tile(const ConvKParams& p, int (&acc)[kTM][kTN],
                                               long long m0, int g, int tg, int warp, int tm,
