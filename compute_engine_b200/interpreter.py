@@ -25,12 +25,14 @@ class Interpreter:
     def __init__(self, flatbuffer_model: bytes, num_threads: int = 1,
                  use_reference_bconv: bool = False, use_indirect_bgemm: bool = False,
                  use_xnnpack: bool = False, batch_size: Optional[int] = None,
-                 use_cuda_graph: bool = True):
+                 use_cuda_graph: bool = True, fuse: bool = True):
         """flatbuffer_model: a serialized LCE model (`.tflite` bytes).
         num_threads / use_xnnpack: accepted for interface parity; the device path has
         no CPU threads to configure. use_reference_bconv / use_indirect_bgemm select
         which of the reference's registrations' validation rules apply (all three run
-        the same CUDA kernel). batch_size: mini-batch used by predict (default: all)."""
+        the same CUDA kernel). batch_size: mini-batch used by predict (default: all).
+        fuse: apply the graph-level fusions (residual-block tail into LceBconv2d's epilogue,
+        max-pool + blur-pool); the outputs are bit-identical either way."""
         if use_reference_bconv and use_indirect_bgemm:
             import warnings
             warnings.warn("'use_reference_bconv' and `use_indirect_bgemm` are both set to true. "
@@ -41,6 +43,7 @@ class Interpreter:
             raise ValueError(f"Could not build the interpreter: {e}") from None
         self.num_threads = num_threads
         self.batch_size = batch_size
+        self.fused_nodes_removed = self._g.fuse_all() if fuse else 0
         self._g.allocate_tensors()
         if use_cuda_graph:
             self._g.enable_cuda_graph(True)
