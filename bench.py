@@ -383,11 +383,15 @@ def graph_workload(args, D):
     sync = g.synchronize
 
     # ---- (1) value: CUDA-graph replay, inputs resident -----------------------------
-    g.enable_cuda_graph(True)
+    g.invoke()                                               # eager: plans (weight tiles) are built
+    g.synchronize()
     launches0 = capi.launch_count()
-    g.invoke()                                               # eager (plans are built)
+    g.invoke()                                               # eager again: exactly one step's kernels
     g.synchronize()
     per_step_launches = capi.launch_count() - launches0
+    g.enable_cuda_graph(True)
+    g.invoke()                                               # the eager pass before the capture
+    g.synchronize()
     W = max(args.warmup, 3)
     for _ in range(W):                                       # capture happens on the first
         g.invoke()
