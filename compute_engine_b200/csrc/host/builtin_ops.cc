@@ -94,6 +94,12 @@ TfLiteStatus ConvPrepare(TfLiteContext* c, TfLiteNode* n) {
                    "DEPTHWISE_CONV_2D: depth_multiplier must be 1");
   int oh, ow;
   B_CAPI(c, lce_b200_f32_conv_out_shape(&d, &oh, &ow));
+  if (!DW && n->outputs->size == 2) {
+    // fused LceQuantize (Graph::FuseFloatGlue): second output = bitpacked signs of the first
+    TfLiteTensor* pk = T(c, n->outputs, 1);
+    B_ENSURE(c, pk && pk->type == kTfLiteInt32, "CONV_2D+LceQuantize: packed output must be int32");
+    if (Resize(c, pk, {d.batch, oh, ow, (d.out_c + 31) / 32}) != kTfLiteOk) return kTfLiteError;
+  }
   return Resize(c, T(c, n->outputs, 0), {d.batch, oh, ow, d.out_c});
 }
 template <bool DW>
@@ -109,6 +115,10 @@ TfLiteStatus ConvInvoke(TfLiteContext* c, TfLiteNode* n) {
   if (DW)
     B_CAPI(c, lce_b200_f32_depthwise_conv2d(&d, in->data.f, f->data.f, bias ? bias->data.f : nullptr,
                                              out->data.f, lce_b200_get_stream()));
+  else if (n->outputs->size == 2)
+    B_CAPI(c, lce_b200_f32_conv2d_packed(&d, in->data.f, f->data.f, bias ? bias->data.f : nullptr,
+                                         out->data.f, T(c, n->outputs, 1)->data.i32,
+                                         lce_b200_get_stream()));
   else
     B_CAPI(c, lce_b200_f32_conv2d(&d, in->data.f, f->data.f, bias ? bias->data.f : nullptr,
                                   out->data.f, lce_b200_get_stream()));

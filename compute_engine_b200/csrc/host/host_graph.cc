@@ -460,12 +460,49 @@ int Graph::FuseStem() {
   return 0;
 }
 
+// CONV_2D (float) whose output also feeds an LceQuantize: the conv emits the packed signs from its
+// epilogue as a second output and the LceQuantize node disappears (first layer of every stage).
+int Graph::FuseConvQuantize() {
+  int removed = 0;
+  for (size_t i = 0; i < nodes_.size(); ++i) {
+    NodeRecord& conv = *nodes_[i];
+    if (conv.name != "builtin:3" || conv.initialized || conv.node.outputs->size != 1) continue;
+    const int y = conv.node.outputs->data[0];
+    if (tensors_[y].type != kTfLiteFloat32) continue;
+    for (size_t k = i + 1; k < nodes_.size(); ++k) {
+      NodeRecord& q = *nodes_[k];
+      if (q.name != "LceQuantize" || q.initialized || q.node.inputs->size != 1 ||
+          q.node.inputs->data[0] != y || q.node.outputs->size != 1)
+        continue;
+      const int packed = q.node.outputs->data[0];
+      if (tensors_[packed].type != kTfLiteInt32) break;
+      std::vector<int> outs{y, packed};
+      LceB200IntArrayFree(conv.node.outputs);
+      conv.node.outputs = MakeDims(outs);
+      conv.name = "CONV_2D+LceQuantize";
+      LceB200IntArrayFree(q.node.inputs);
+      LceB200IntArrayFree(q.node.outputs);
+      LceB200IntArrayFree(q.node.temporaries);
+      LceB200IntArrayFree(q.node.intermediates);
+      nodes_.erase(nodes_.begin() + k);
+      ++removed;
+      allocated_ = false;
+      break;
+    }
+  }
+  return removed;
+}
+
 int Graph::FuseFloatGlue() {
   if (!device_arena_) return 0;
   // the one-pass stem is correct (bit-identical) but not yet faster than its three kernels
   // (same instruction count, they are not memory bound): opt-in until it is
   const char* stem_env = getenv("LCE_B200_FUSE_STEM");
   int removed = (stem_env && stem_env[0] == '1') ? FuseStem() : 0;
+  // same verdict for CONV_2D -> LceQuantize: bit-identical, but the stand-alone pack kernel already
+  // streams at ~6 TB/s and the epilogue version saves nothing measurable (2.457 vs 2.436 ms/step)
+  const char* cq_env = getenv("LCE_B200_FUSE_CONV_QUANT");
+  if (cq_env && cq_env[0] == '1') removed += FuseConvQuantize();
   for (size_t i = 0; i < nodes_.size(); ++i) {
     NodeRecord& pool = *nodes_[i];
     if (pool.name != "builtin:17" || pool.initialized ||

@@ -75,9 +75,11 @@ class Graph {
 
   // Fusions among the float builtins around the binary path:
   //   MAX_POOL_2D(2x2, stride 1, VALID) -> DEPTHWISE_CONV_2D(3x3)  =>  one node
-  //   CONV_2D(3x3 s2 -> 16) -> DEPTHWISE_CONV_2D(3x3 s2) -> CONV_2D(1x1 -> 64)  =>  one node
+  //   CONV_2D(3x3 s2 -> 16) -> DEPTHWISE_CONV_2D(3x3 s2) -> CONV_2D(1x1 -> 64)  =>  one node (opt-in)
+  //   CONV_2D -> LceQuantize  =>  the conv writes the packed signs as a second output
   // (QuickNet's anti-aliased down-sampling). Bit-identical. Returns the nodes removed.
   int FuseFloatGlue();
+  int FuseConvQuantize();  // part of FuseFloatGlue: CONV_2D -> LceQuantize => conv with 2 outputs
   int FuseStem();  // part of FuseFloatGlue: stem conv + depthwise + pointwise conv -> one node
 
   // init (first time) + prepare of every node in order, then arena allocation.

@@ -12,6 +12,7 @@
 #include <cstdint>
 #include <cstdlib>
 
+#include "lce_b200.h"
 #include "lce_b200_builtins.h"
 
 namespace lce_b200_internal {
@@ -74,7 +75,8 @@ __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restr
                                                             const float* __restrict__ filter,
                                                             const float* __restrict__ bias,
                                                             float* __restrict__ out, ConvGeom g,
-                                                            long long M, int G, int tiles_per_block) {
+                                                            long long M, int G, int tiles_per_block,
+                                                            int32_t* __restrict__ packed) {
   extern __shared__ __align__(16) float w_s[];   // [K][G][20] then bias [G][16]
   const int KH = KH_ ? KH_ : g.KH, KW = KW_ ? KW_ : g.KW, CIN = CIN_ ? CIN_ : g.Cin;
   const int K = KH * KW * CIN;
@@ -190,19 +192,31 @@ __global__ void __launch_bounds__(128) conv_direct16_kernel(const float* __restr
   const float* bb = b_s + c0;
 #pragma unroll
   for (int p = 0; p < kPX; ++p) {
-    if (!ok[p]) continue;
     const long long m = static_cast<long long>(blk_m0) + p * px_per_blk + lpx;
-    float* o = out + m * g.Cout + c0;
-    if (c0 + 16 <= g.Cout && (g.Cout & 3) == 0) {
+    uint32_t bits = 0;
+    if (ok[p]) {
+      float* o = out + m * g.Cout + c0;
+      if (c0 + 16 <= g.Cout && (g.Cout & 3) == 0) {
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        reinterpret_cast<float4*>(o)[q] =
-            make_float4(apply_act(acc[p][4 * q] + bb[4 * q], g.act),
-                        apply_act(acc[p][4 * q + 1] + bb[4 * q + 1], g.act),
-                        apply_act(acc[p][4 * q + 2] + bb[4 * q + 2], g.act),
-                        apply_act(acc[p][4 * q + 3] + bb[4 * q + 3], g.act));
-    } else {
-      for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[p][c] + bb[c], g.act);
+        for (int q = 0; q < 4; ++q) {
+          const float4 v = make_float4(apply_act(acc[p][4 * q] + bb[4 * q], g.act),
+                                       apply_act(acc[p][4 * q + 1] + bb[4 * q + 1], g.act),
+                                       apply_act(acc[p][4 * q + 2] + bb[4 * q + 2], g.act),
+                                       apply_act(acc[p][4 * q + 3] + bb[4 * q + 3], g.act));
+          reinterpret_cast<float4*>(o)[q] = v;
+          bits |= ((v.x < 0.0f ? 1u : 0u) | (v.y < 0.0f ? 2u : 0u) | (v.z < 0.0f ? 4u : 0u) |
+                   (v.w < 0.0f ? 8u : 0u)) << (4 * q);
+        }
+      } else {
+        for (int c = 0; c < 16 && c0 + c < g.Cout; ++c) o[c] = apply_act(acc[p][c] + bb[c], g.act);
+      }
+    }
+    if (packed != nullptr) {
+      // fused LceQuantize (host guarantees Cout % 32 == 0 and an even group count): lanes gi and
+      // gi ^ 1 are neighbours and hold the two halves of one word; every lane runs the shuffle
+      uint32_t v = bits << ((gi & 1) * 16);
+      v |= __shfl_xor_sync(0xffffffffu, v, 1);
+      if (ok[p] && (gi & 1) == 0) packed[m * (g.Cout >> 5) + (gi >> 1)] = static_cast<int32_t>(v);
     }
   }
   }  // tile
@@ -215,7 +229,8 @@ __global__ void __launch_bounds__(256, 2) conv_gemm128_kernel(const float* __res
                                                            const float* __restrict__ Wt,
                                                            const float* __restrict__ bias,
                                                            float* __restrict__ out, long long M,
-                                                           int N, int K, int act) {
+                                                           int N, int K, int act,
+                                                           int32_t* __restrict__ packed) {
   __shared__ __align__(16) float A_s[2][kPK][kPM + 4];
   __shared__ __align__(16) float B_s[2][kPK][kPN + 4];
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
@@ -280,7 +295,7 @@ __global__ void __launch_bounds__(256, 2) conv_gemm128_kernel(const float* __res
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const long long m = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-    if (m >= M) continue;
+    const bool row_ok = m < M;
 #pragma unroll
     for (int jh = 0; jh < 2; ++jh) {
       const int n = n0 + jh * 64 + tx * 4;
@@ -288,10 +303,22 @@ __global__ void __launch_bounds__(256, 2) conv_gemm128_kernel(const float* __res
 #pragma unroll
       for (int q = 0; q < 4; ++q)
         v[q] = apply_act(acc[i][jh * 4 + q] + ((bias && n + q < N) ? bias[n + q] : 0.0f), act);
-      float* o = out + m * N + n;
-      if (n + 3 < N && (N & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
-      else
-        for (int q = 0; q < 4 && n + q < N; ++q) o[q] = v[q];
+      if (row_ok) {
+        float* o = out + m * N + n;
+        if (n + 3 < N && (N & 3) == 0) *reinterpret_cast<float4*>(o) = make_float4(v[0], v[1], v[2], v[3]);
+        else
+          for (int q = 0; q < 4 && n + q < N; ++q) o[q] = v[q];
+      }
+      if (packed != nullptr) {
+        // fused LceQuantize (host guarantees N % 32 == 0): the 8 lanes tx & 7 = 0..7 hold one word
+        uint32_t w = ((v[0] < 0.0f ? 1u : 0u) | (v[1] < 0.0f ? 2u : 0u) | (v[2] < 0.0f ? 4u : 0u) |
+                      (v[3] < 0.0f ? 8u : 0u)) << ((tx & 7) * 4);
+        w |= __shfl_xor_sync(0xffffffffu, w, 1);
+        w |= __shfl_xor_sync(0xffffffffu, w, 2);
+        w |= __shfl_xor_sync(0xffffffffu, w, 4);
+        if (row_ok && (tx & 7) == 0 && n < N)
+          packed[m * (N >> 5) + ((n0 + jh * 64) >> 5) + (tx >> 3)] = static_cast<int32_t>(w);
+      }
     }
   }
 }
@@ -1188,8 +1215,11 @@ int lce_b200_f32_conv_out_shape(const lce_f32_conv_desc* d, int* out_h, int* out
   return 0;
 }
 
-int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float* filter,
-                        const float* bias, float* out, void* stream) {
+// `packed` (optional): LceQuantize of the output. Kernels that can emit it in their epilogue do
+// and set *packed_done; the caller packs with the stand-alone kernel otherwise.
+static int conv2d_impl(const lce_f32_conv_desc* d, const float* in, const float* filter,
+                       const float* bias, float* out, int32_t* packed, bool* packed_done,
+                       void* stream) {
   ConvGeom g;
   if (make_geom(d, &g)) return 1;
   const long long M = static_cast<long long>(g.B) * g.OH * g.OW;
@@ -1238,8 +1268,11 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
     const unsigned blocks = static_cast<unsigned>((tiles + tpb - 1) / tpb);
     (void)threads;
     cudaStream_t st = as_stream(stream);
+    // fused LceQuantize: whole words per pixel, lane pairs hold the two halves of a word
+    int32_t* pk = (packed && (g.Cout & 31) == 0 && (G & 1) == 0 && 128 % G == 0) ? packed : nullptr;
+    if (pk) *packed_done = true;
 #define LCE_DIRECT(KH_, KW_, CIN_, PX_) \
-  conv_direct16_kernel<KH_, KW_, CIN_, PX_><<<blocks, 128, smem, st>>>(in, filter, bias, out, g, M, G, tpb)
+  conv_direct16_kernel<KH_, KW_, CIN_, PX_><<<blocks, 128, smem, st>>>(in, filter, bias, out, g, M, G, tpb, pk)
     if (stem) {
       if (PX == 1) LCE_DIRECT(3, 3, 3, 1);
       else if (PX == 2) LCE_DIRECT(3, 3, 3, 2);
@@ -1249,7 +1282,7 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
       else if (PX == 2) LCE_DIRECT(1, 1, 16, 2);
       else
         conv_direct16_kernel<1, 1, 16, 4, true><<<blocks, 128, smem, st>>>(in, filter, bias, out, g,
-                                                                           M, G, tpb);
+                                                                           M, G, tpb, pk);
     } else {
       LCE_DIRECT(0, 0, 0, 4);
     }
@@ -1266,8 +1299,10 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   }
   if (plain) {
     dim3 grid(static_cast<unsigned>((M + kPM - 1) / kPM), (g.Cout + kPN - 1) / kPN);
+    int32_t* pk = (packed && (g.Cout & 31) == 0) ? packed : nullptr;
+    if (pk) *packed_done = true;
     conv_gemm128_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, M, g.Cout, K,
-                                                             g.act);
+                                                             g.act, pk);
     return launch_check("conv_gemm128_kernel");
   }
   if (K <= kIKMax && static_cast<long long>(g.H) * g.W * g.Cin < (1LL << 31)) {
@@ -1287,6 +1322,24 @@ int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float
   dim3 grid(static_cast<unsigned>((M + kGM - 1) / kGM), (g.Cout + kGN - 1) / kGN);
   conv_gemm_kernel<<<grid, 256, 0, as_stream(stream)>>>(in, filter, bias, out, g, M);
   return launch_check("conv_gemm_kernel");
+}
+
+int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in, const float* filter,
+                        const float* bias, float* out, void* stream) {
+  bool done = false;
+  return conv2d_impl(d, in, filter, bias, out, nullptr, &done, stream);
+}
+
+int lce_b200_f32_conv2d_packed(const lce_f32_conv_desc* d, const float* in, const float* filter,
+                               const float* bias, float* out, int32_t* packed_out, void* stream) {
+  if (!packed_out) return lce_b200_f32_conv2d(d, in, filter, bias, out, stream);
+  bool done = false;
+  if (conv2d_impl(d, in, filter, bias, out, packed_out, &done, stream)) return 1;
+  if (done) return 0;
+  int oh, ow;
+  if (lce_b200_f32_conv_out_shape(d, &oh, &ow)) return 1;
+  return lce_b200_quantize(LCE_T_FLOAT, out, static_cast<int64_t>(d->batch) * oh * ow, d->out_c, 0,
+                           packed_out, stream);
 }
 
 int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in,

@@ -39,6 +39,12 @@ typedef struct lce_f32_pool_desc {
 int lce_b200_f32_conv_out_shape(const lce_f32_conv_desc* d, int* out_h, int* out_w);
 int lce_b200_f32_conv2d(const lce_f32_conv_desc* d, const float* in_dev, const float* filter_dev,
                         const float* bias_dev, float* out_dev, void* stream);
+/* conv2d + LceQuantize of its output in one call: packed_out[pixel][ceil(out_c/32)] gets the sign
+ * bits of `out` (bit = value < 0, tail bits 0), from the convolution's epilogue where the kernel
+ * allows it, else by the stand-alone pack kernel. Identical to conv2d followed by lce_b200_quantize. */
+int lce_b200_f32_conv2d_packed(const lce_f32_conv_desc* d, const float* in_dev,
+                               const float* filter_dev, const float* bias_dev, float* out_dev,
+                               int32_t* packed_out_dev, void* stream);
 /* depth_multiplier 1; filter [1, fh, fw, C]; d->out_c == d->in_c */
 int lce_b200_f32_depthwise_conv2d(const lce_f32_conv_desc* d, const float* in_dev,
                                   const float* filter_dev, const float* bias_dev,

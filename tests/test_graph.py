@@ -210,21 +210,30 @@ def test_residual_block_fusion_rewrites_the_graph():
     g.close()
 
 
-def test_stem_fusion_is_opt_in(monkeypatch):
-    """LCE_B200_FUSE_STEM=1: conv 3x3 s2 -> depthwise 3x3 s2 -> conv 1x1 of the stem as one node."""
+def test_opt_in_fusions(monkeypatch):
+    """LCE_B200_FUSE_STEM=1: conv 3x3 s2 -> depthwise 3x3 s2 -> conv 1x1 of the stem as one node;
+    LCE_B200_FUSE_CONV_QUANT=1: CONV_2D -> LceQuantize as a conv with a second, bitpacked output."""
+    monkeypatch.setenv("LCE_B200_FUSE_CONV_QUANT", "1")
+    g = H.HostGraph.from_tflite(zoo.quicknet(batch=1, image=64, seed=3), device_arena=True)
+    assert g.fuse_all() == 28 + 3 + 4 and g.num_nodes() == 29
+    names = [g.node_name(i) for i in range(g.num_nodes())]
+    assert names.count("CONV_2D+LceQuantize") == 4 and "LceQuantize" not in names
+    g.close()
     monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")
     g = H.HostGraph.from_tflite(zoo.quicknet(batch=1, image=64, seed=3), device_arena=True)
-    assert g.fuse_all() == 28 + 5 and g.num_nodes() == 31
+    assert g.fuse_all() == 28 + 5 + 3 and g.num_nodes() == 28
     names = [g.node_name(i) for i in range(g.num_nodes())]
     assert names[0] == "CONV_2D+DEPTHWISE_CONV_2D+CONV_2D" and "builtin:4" not in names
-    assert names.count("builtin:3") == 3               # the transitions' 1x1 convs
+    assert names.count("CONV_2D+LceQuantize") == 3     # the transitions' 1x1 convs
+    assert names.count("LceQuantize") == 1             # after the fused stem
     g.close()
 
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("family,image", [("quicknet", 64), ("quicknet", 88), ("birealnet18", 64)])
 def test_gpu_fused_graph_is_bit_identical_to_unfused(family, image, monkeypatch):
-    monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")       # include the opt-in stem fusion
+    monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")       # include the opt-in fusions
+    monkeypatch.setenv("LCE_B200_FUSE_CONV_QUANT", "1")
     blob = zoo.MODELS[family](batch=1, image=image, seed=11)
     x = np.random.default_rng(4).standard_normal((5, image, image, 3)).astype(np.float32)
     outs = []
@@ -232,7 +241,7 @@ def test_gpu_fused_graph_is_bit_identical_to_unfused(family, image, monkeypatch)
         g = H.HostGraph.from_tflite(blob, device_arena=True)
         if fuse:
             assert g.fuse_residual_blocks() > 0
-            assert g.fuse_float_glue() == (5 if family == "quicknet" else 0)
+            assert g.fuse_float_glue() == (5 + 3 if family == "quicknet" else 0)
         g.resize_input(g.inputs()[0], x.shape)
         g.allocate_tensors()
         g.enable_cuda_graph(True)
