@@ -63,16 +63,18 @@ __host__ __device__ __forceinline__ uint32_t imma_weight_bytes(uint32_t nibble) 
   return ((nibble & 0xFu) * 0x00204081u & 0x01010101u) * 0xFEu + 0x01010101u;
 }
 
-// Plan-time: wtx[n_tile][k word][ns][lane] = {b0, b1}, the B fragment (k-step = that word,
-// channels ns*8 .. ns*8+7 of the tile) of `lane`. Channels past the group's end read as 0 words.
+// Plan-time: wtx[n_tile][k word][ns / 2][lane][ns & 1] = {b0, b1}, the B fragment (k-step = that
+// word, channels ns*8 .. ns*8+7 of the tile) of `lane`; the fragments of two neighbouring
+// sub-tiles sit side by side so one 128-bit LDS fetches both. Channels past the group's end read
+// as 0 words.
 __global__ void expand_weights_imma_kernel(const int32_t* __restrict__ filter,
                                            uint2* __restrict__ wtx, int cout_pg,
                                            int tiles_per_group, int taps, int Cw_pg,
                                            long long total) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
-  const int lane = static_cast<int>(idx & 31);
-  const int ns = static_cast<int>((idx >> 5) & 7);
+  const int ns = static_cast<int>(((idx >> 6) & 3) * 2 + (idx & 1));   // idx = ((kw*4 + ns/2)*32 + lane)*2 + (ns&1)
+  const int lane = static_cast<int>((idx >> 1) & 31);
   const int Kw = taps * Cw_pg;
   const long long r = idx >> 8;
   const int kw = static_cast<int>(r % Kw);
@@ -90,10 +92,10 @@ template <int V>
 __device__ __forceinline__ void compute_chunk_imma(const typename VecT<V>::T* A_s,
                                                    const uint2* B_s, int nkv, int warp, int gid,
                                                    int tig, int lane, int (&acc)[2][8][4]) {
+  const uint4* b4_base = reinterpret_cast<const uint4*>(B_s) + lane;
   using Vec = typename VecT<V>::T;
   const uint32_t sel = 0x4440u | static_cast<uint32_t>(tig);
   const Vec* a_base = A_s + warp * 32 + gid;
-  const uint2* b_base = B_s + lane;
 #pragma unroll 1
   for (int kv = 0; kv < nkv; ++kv) {
     uint32_t r[2][2][V];   // [m sub-tile][row gid / gid + 8][word]
@@ -117,10 +119,12 @@ __device__ __forceinline__ void compute_chunk_imma(const typename VecT<V>::T* A_
 #pragma unroll
       for (int q = 0; q < H; ++q) {
 #pragma unroll
-        for (int ns = 0; ns < 8; ++ns) {
-          const uint2 b = b_base[((kv * V + qh + q) * 8 + ns) * 32];
-          mma_u8s8(acc[0][ns], a[q][0], b.x, b.y);
-          mma_u8s8(acc[1][ns], a[q][1], b.x, b.y);
+        for (int np = 0; np < 4; ++np) {
+          const uint4 b = b4_base[((kv * V + qh + q) * 4 + np) * 32];
+          mma_u8s8(acc[0][2 * np], a[q][0], b.x, b.y);
+          mma_u8s8(acc[1][2 * np], a[q][1], b.x, b.y);
+          mma_u8s8(acc[0][2 * np + 1], a[q][0], b.z, b.w);
+          mma_u8s8(acc[1][2 * np + 1], a[q][1], b.z, b.w);
         }
       }
     }
