@@ -15,6 +15,10 @@
 // so the accumulators start at the per-channel popcount of the filter row and the tensor pipe
 // adds the signed dot product -- the same integer the XOR+POPC kernel produces, bit for bit
 // (out-of-bounds taps gather 0 words = "+1" padding exactly as before).
+// To make the bits -> bytes expansion cheap, bit i of a nibble becomes the byte VALUE 2^i (one
+// PRMT replicates the thread's byte into all four lanes of a register, one AND with 0x08040201
+// isolates bit i in byte i) and the weight byte at that k position is +-(8 >> i): every product
+// is +-8, the accumulators hold 8 * popc(a ^ w) exactly, and the epilogue's "<< 1" becomes ">> 2".
 // Activations are expanded bits -> bytes in registers, per warp. The static weights are expanded
 // once per plan into mma B-fragment order (8 bytes per lane, k-step and 8-channel sub-tile) and
 // reach shared memory by TMA bulk copy, so a B fragment is one conflict-free 64-bit LDS.
@@ -43,11 +47,12 @@ constexpr int kIBytesPerWord = kIBM * 4 + 8 * 32 * 8;  // smem per K word: packe
 // TMA-copied while chunk c is multiplied. The host sizes the chunks (imma_smem_budget):
 // 3 CTAs per SM for the uint4 instances (153 registers), 4 for the narrower ones (128).
 
-// byte `tig` of w -> two registers of four u8 each: bit i of the low / high nibble -> byte i
+// byte `tig` of w -> two registers of four u8 each: bit i of the low / high nibble -> byte i with
+// value 2^i (sel = tig * 0x1111 replicates the byte; 4 ALU instructions, no multiplies)
 __device__ __forceinline__ void expand01(uint32_t w, uint32_t sel, uint32_t& lo, uint32_t& hi) {
-  const uint32_t byte = __byte_perm(w, 0u, sel);
-  lo = ((byte & 0x0Fu) * 0x00204081u) & 0x01010101u;
-  hi = ((byte >> 4) * 0x00204081u) & 0x01010101u;
+  const uint32_t t = __byte_perm(w, 0u, sel);
+  lo = t & 0x08040201u;
+  hi = (t >> 4) & 0x08040201u;
 }
 __device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], uint32_t b0,
                                          uint32_t b1) {
@@ -58,9 +63,15 @@ __device__ __forceinline__ void mma_u8s8(int (&c)[4], const uint32_t (&a)[4], ui
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// spread(bit i of a nibble -> byte i) and map bit -> +1 / -1
+// weight nibble -> four s8: byte i = +(8 >> i) for bit 0 (+1), -(8 >> i) for bit 1 (-1)
 __host__ __device__ __forceinline__ uint32_t imma_weight_bytes(uint32_t nibble) {
-  return ((nibble & 0xFu) * 0x00204081u & 0x01010101u) * 0xFEu + 0x01010101u;
+  uint32_t r = 0;
+  for (int i = 0; i < 4; ++i) {
+    const int mag = 8 >> i;
+    const int v = ((nibble >> i) & 1u) ? -mag : mag;
+    r |= (static_cast<uint32_t>(v) & 0xFFu) << (8 * i);
+  }
+  return r;
 }
 
 // Plan-time: wtx[n_tile][k word][ns / 2][lane][ns & 1] = {b0, b1}, the B fragment (k-step = that
@@ -94,7 +105,7 @@ __device__ __forceinline__ void compute_chunk_imma(const typename VecT<V>::T* A_
                                                    int tig, int lane, int (&acc)[2][8][4]) {
   const uint4* b4_base = reinterpret_cast<const uint4*>(B_s) + lane;
   using Vec = typename VecT<V>::T;
-  const uint32_t sel = 0x4440u | static_cast<uint32_t>(tig);
+  const uint32_t sel = 0x1111u * static_cast<uint32_t>(tig);
   const Vec* a_base = A_s + warp * 32 + gid;
 #pragma unroll 1
   for (int kv = 0; kv < nkv; ++kv) {
@@ -132,7 +143,8 @@ __device__ __forceinline__ void compute_chunk_imma(const typename VecT<V>::T* A_
 }
 
 // SAME padding with pad value 0 (reference.h:100-103), for this kernel's accumulator layout:
-// an out-of-bounds tap contributes channels_in_per_group / 2 instead of popc(0 ^ w).
+// an out-of-bounds tap contributes channels_in_per_group / 2 instead of popc(0 ^ w) -- times 8,
+// the accumulators' scale.
 __device__ __forceinline__ void zero_pad_correction_imma(const ConvKParams& p,
                                                          int (&acc)[2][8][4], long long m0,
                                                          int c_tile, int warp, int gid, int tig) {
@@ -160,8 +172,9 @@ __device__ __forceinline__ void zero_pad_correction_imma(const ConvKParams& p,
 #pragma unroll
           for (int ns = 0; ns < 8; ++ns) {
             const int c = c_tile + ns * 8 + tig * 2;
-            acc[ms][ns][h * 2] += p.zp_half - p.tap_popc[static_cast<size_t>(c) * taps + t];
-            acc[ms][ns][h * 2 + 1] += p.zp_half - p.tap_popc[static_cast<size_t>(c + 1) * taps + t];
+            acc[ms][ns][h * 2] += 8 * (p.zp_half - p.tap_popc[static_cast<size_t>(c) * taps + t]);
+            acc[ms][ns][h * 2 + 1] +=
+                8 * (p.zp_half - p.tap_popc[static_cast<size_t>(c + 1) * taps + t]);
           }
         }
       }
@@ -205,7 +218,7 @@ __device__ __forceinline__ void epilogue_imma(const ConvKParams& p, int (&acc)[2
 #pragma unroll
           for (int ns = 0; ns < 8; ++ns)
             *reinterpret_cast<int2*>(o + ns * 8) =
-                make_int2(acc[ms][ns][h * 2], acc[ms][ns][h * 2 + 1]);
+                make_int2(acc[ms][ns][h * 2] >> 3, acc[ms][ns][h * 2 + 1] >> 3);
         }
         continue;
       }
@@ -214,10 +227,11 @@ __device__ __forceinline__ void epilogue_imma(const ConvKParams& p, int (&acc)[2
         float y[16];
 #pragma unroll
         for (int ns = 0; ns < 8; ++ns) {
-          y[2 * ns] = transform_float(acc[ms][ns][h * 2], p.clamp_min, p.clamp_max, mul_r[ns].x,
-                                      bias_r[ns].x);
-          y[2 * ns + 1] = transform_float(acc[ms][ns][h * 2 + 1], p.clamp_min, p.clamp_max,
-                                          mul_r[ns].y, bias_r[ns].y);
+          // accumulators hold 8 * acc: OutputTransform's (acc << 1) is (acc8 >> 2), exactly
+          y[2 * ns] = transform_float_x2(acc[ms][ns][h * 2] >> 2, p.clamp_min, p.clamp_max,
+                                         mul_r[ns].x, bias_r[ns].x);
+          y[2 * ns + 1] = transform_float_x2(acc[ms][ns][h * 2 + 1] >> 2, p.clamp_min, p.clamp_max,
+                                            mul_r[ns].y, bias_r[ns].y);
         }
         if (has_res) {
           // (A TMA-staged copy of the shortcut tile was measured slower on every layer: the
@@ -290,15 +304,15 @@ bconv_imma_kernel(const ConvKParams p) {
   }
   __syncthreads();
 
-  // accumulators start at popc(filter row): acc = popc(w) + sum a * w'
+  // accumulators start at 8 * popc(filter row): acc8 = 8 * (popc(w) + sum a * w')
   int acc[2][8][4];
 #pragma unroll
   for (int ns = 0; ns < 8; ++ns) {
     const int2 pw = *reinterpret_cast<const int2*>(p.wpop + c_tile + ns * 8 + tig * 2);
 #pragma unroll
     for (int ms = 0; ms < 2; ++ms) {
-      acc[ms][ns][0] = pw.x; acc[ms][ns][1] = pw.y;
-      acc[ms][ns][2] = pw.x; acc[ms][ns][3] = pw.y;
+      acc[ms][ns][0] = pw.x * 8; acc[ms][ns][1] = pw.y * 8;
+      acc[ms][ns][2] = pw.x * 8; acc[ms][ns][3] = pw.y * 8;
     }
   }
   if (OUT == LCE_OUT_FLOAT && p.residual != nullptr) {

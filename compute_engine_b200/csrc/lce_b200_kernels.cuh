@@ -222,6 +222,12 @@ __device__ __forceinline__ float transform_float(int acc, int cmin, int cmax, fl
   x = max(min(x, cmax), cmin);
   return __fadd_rn(__fmul_rn(static_cast<float>(x), mul), bias);
 }
+// the same with the doubled accumulator (acc << 1) already formed by the caller
+__device__ __forceinline__ float transform_float_x2(int x, int cmin, int cmax, float mul,
+                                                    float bias) {
+  x = max(min(x, cmax), cmin);
+  return __fadd_rn(__fmul_rn(static_cast<float>(x), mul), bias);
+}
 // core::round (std::round, ties away) + x86 cvttss2si semantics + saturate,
 // types.h:50-94, output_transform.h:132-143.
 __device__ __forceinline__ int round_saturate_i8(float y) {
