@@ -1,0 +1,451 @@
+// tc_probe.cu -- building-block probe for the tcgen05 binary-conv kernel (sm_100a).
+// Nothing here is on the product path: it pins, on a real B200, the hardware conventions the
+// kernel in compute_engine_b200/csrc/lce_b200_tc.cuh relies on, each against a CPU loop:
+//   T1  tcgen05.mma kind::i8, A and B from shared memory (no-swizzle K-major core matrices):
+//       instruction descriptor, shared-memory descriptor (LBO / SBO meaning), D layout in TMEM
+//   T2  the same product with A written to TMEM by tcgen05.st.32x32b (row = lane, 4 k per column)
+//   T3  TMA tensor maps: 1-D int32 map with an unaligned start and an out-of-bounds tail,
+//       2-D float map with SWIZZLE_128B (load, raw dump, store)
+//   T4  MMA issue rate for N = 64 / 128 / 256, A from shared memory and from TMEM
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tc_probe tools/tc_probe.cu
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <vector>
+
+#define CK(x)                                                                         \
+  do {                                                                                \
+    cudaError_t e_ = (x);                                                             \
+    if (e_ != cudaSuccess) {                                                          \
+      printf("CUDA error %s at %s:%d: %s\n", #x, __FILE__, __LINE__, cudaGetErrorString(e_)); \
+      exit(2);                                                                        \
+    }                                                                                 \
+  } while (0)
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n.reg .pred p;\nWAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\nbra WAIT_%=;\nDONE_%=:\n}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"r"(taddr),
+               "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void mma_i8_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__host__ __device__ inline uint64_t make_sdesc(uint32_t saddr, uint32_t lbo, uint32_t sbo, uint32_t layout) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(lbo >> 4) << 16) |
+         (static_cast<uint64_t>(sbo >> 4) << 32) | (1ull << 46) | (static_cast<uint64_t>(layout) << 61);
+}
+__host__ __device__ inline uint32_t make_idesc_i8(int M, int N, int a_signed, int b_signed) {
+  return (2u << 4) | (static_cast<uint32_t>(a_signed) << 7) | (static_cast<uint32_t>(b_signed) << 10) |
+         (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// no-swizzle K-major image: 8 x 16 B core matrices; along K adjacent (128 B), 8-row groups at (K/16)*128
+__host__ __device__ inline int core_off(int row, int kb, int K) {
+  return (row >> 3) * (K / 16) * 128 + (kb >> 4) * 128 + (row & 7) * 16 + (kb & 15);
+}
+
+// ------------------------------------------------------------------ T1 / T2
+// mode 0: A from smem (SS).  mode 1: A from TMEM (TS), written with tcgen05.st.
+// swap = 1 exchanges the LBO / SBO descriptor fields (hypothesis test).
+__global__ void __launch_bounds__(128) probe_mma(const int8_t* __restrict__ A_img, const int8_t* __restrict__ B_img,
+                                                 const int8_t* __restrict__ A_rows, int32_t* __restrict__ D, int mode,
+                                                 int swap, int N, int K, int a_signed) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  unsigned char* As = smem;
+  unsigned char* Bs = smem + 128 * K;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 128 * K / 16; i += 128) reinterpret_cast<uint4*>(As)[i] = reinterpret_cast<const uint4*>(A_img)[i];
+  for (int i = tid; i < N * K / 16; i += 128) reinterpret_cast<uint4*>(Bs)[i] = reinterpret_cast<const uint4*>(B_img)[i];
+  fence_proxy_async();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  const uint32_t d_t = tb;             // columns [0, N)
+  const uint32_t a_t = tb + 256;       // columns [256, 256 + K/4)
+  const uint32_t lane_base = static_cast<uint32_t>(warp * 32) << 16;
+  if (mode == 1) {
+    const int r = tid;
+    for (int c0 = 0; c0 < K / 4; c0 += 8) {
+      uint32_t v[8];
+      for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint32_t*>(A_rows + r * K + (c0 + j) * 4);
+      tmem_st8(a_t + lane_base + c0, v);
+    }
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_i8(128, N, a_signed, 1);
+    const uint32_t lbo = 128, sbo = (K / 16) * 128;
+    for (int ks = 0; ks < K / 32; ++ks) {
+      const uint64_t bd = swap ? make_sdesc(smem_u32(Bs) + ks * 256, sbo, lbo, 0) : make_sdesc(smem_u32(Bs) + ks * 256, lbo, sbo, 0);
+      if (mode == 0) {
+        const uint64_t ad = swap ? make_sdesc(smem_u32(As) + ks * 256, sbo, lbo, 0) : make_sdesc(smem_u32(As) + ks * 256, lbo, sbo, 0);
+        mma_i8_ss(d_t, ad, bd, idesc, ks > 0);
+      } else {
+        mma_i8_ts(d_t, a_t + ks * 8, bd, idesc, ks > 0);
+      }
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t v[8];
+    tmem_ld8(d_t + lane_base + c0, v);
+    for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = static_cast<int32_t>(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------ T4: issue rate
+__global__ void __launch_bounds__(128) probe_rate(int mode, int N, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01ff01ffu, 0, 0x02020202u);
+  fence_proxy_async();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  {
+    uint32_t v[8] = {0x01010101u, 0, 0x01000100u, 0, 1, 2, 3, 4};
+    for (int c = 0; c < 32; c += 8) tmem_st8(tb + 256 + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  long long t0 = 0;
+  if (tid == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_i8(128, N, 1, 1);
+    const uint32_t As = smem_u32(smem), Bs = smem_u32(smem + 128 * 128);
+    t0 = clock64();
+    for (int it = 0; it < iters; ++it) {
+      const int ks = it & 3;
+      const uint64_t bd = make_sdesc(Bs + ks * 256, 128, 1024, 0);
+      if (mode == 0) mma_i8_ss(tb + (it & 1) * 256 * 0, make_sdesc(As + ks * 256, 128, 1024, 0), bd, idesc, 1);
+      else mma_i8_ts(tb, tb + 256 + ks * 8, bd, idesc, 1);
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+// ------------------------------------------------------------------ T3: TMA
+__global__ void probe_tma1d(const __grid_constant__ CUtensorMap tm, int c0, int nbox, int32_t* out) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    fence_proxy_async();
+    mbar_expect_tx(&bar, nbox * 1024);
+    for (int i = 0; i < nbox; ++i)
+      asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];" ::"r"(smem_u32(smem + i * 1024)),
+                   "l"(reinterpret_cast<uint64_t>(&tm)), "r"(smem_u32(&bar)), "r"(c0 + i * 256) : "memory");
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < nbox * 256; i += blockDim.x) out[i] = reinterpret_cast<int32_t*>(smem)[i];
+}
+
+__global__ void probe_tma2d(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_out, int col0, int row0,
+                            float* raw_dump) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  float* in_s = reinterpret_cast<float*>(smem);           // 32 rows x 128 B
+  float* out_s = reinterpret_cast<float*>(smem + 4096);
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(&bar, 4096);
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(in_s)),
+                 "l"(reinterpret_cast<uint64_t>(&tm_in)), "r"(smem_u32(&bar)), "r"(col0), "r"(row0) : "memory");
+  }
+  __syncthreads();
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < 1024; i += blockDim.x) raw_dump[i] = in_s[i];
+  // thread t = row t: read its row through the hypothesised swizzle, write 2x into out_s the same way
+  if (threadIdx.x < 32) {
+    const int r = threadIdx.x;
+    for (int ch = 0; ch < 8; ++ch) {
+      const int phys = r * 128 + ((ch ^ (r & 7)) << 4);
+      float4 v = *reinterpret_cast<const float4*>(smem + phys);
+      v.x *= 2.f; v.y *= 2.f; v.z *= 2.f; v.w *= 2.f;
+      *reinterpret_cast<float4*>(smem + 4096 + phys) = v;
+    }
+  }
+  fence_proxy_async();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(&tm_out)),
+                 "r"(smem_u32(out_s)), "r"(col0), "r"(row0) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+  if (!fn) { printf("cuTensorMapEncodeTiled not found\n"); exit(2); }
+  return reinterpret_cast<EncodeTiledFn>(fn);
+}
+
+static int run_mma_case(int mode, int swap, int N, int K, int a_signed, bool verbose) {
+  std::vector<int8_t> A(128 * K), B(N * K), Aimg(128 * K), Bimg(N * K);
+  srand(1234 + N + K);
+  for (auto& v : A) v = a_signed ? static_cast<int8_t>((rand() % 17) - 8) : static_cast<int8_t>(rand() % 9);
+  for (auto& v : B) v = static_cast<int8_t>((rand() % 17) - 8);
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < K; ++k) Aimg[core_off(r, k, K)] = A[r * K + k];
+  for (int n = 0; n < N; ++n)
+    for (int k = 0; k < K; ++k) Bimg[core_off(n, k, K)] = B[n * K + k];
+  int8_t *dA, *dB, *dAr; int32_t* dD;
+  CK(cudaMalloc(&dA, Aimg.size())); CK(cudaMalloc(&dB, Bimg.size())); CK(cudaMalloc(&dAr, A.size()));
+  CK(cudaMalloc(&dD, 128 * N * 4));
+  CK(cudaMemcpy(dA, Aimg.data(), Aimg.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bimg.data(), Bimg.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dAr, A.data(), A.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemset(dD, 0xEE, 128 * N * 4));
+  const size_t smem = (128 + N) * K;
+  CK(cudaFuncSetAttribute(probe_mma, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+  probe_mma<<<1, 128, smem>>>(dA, dB, dAr, dD, mode, swap, N, K, a_signed);
+  cudaError_t e = cudaDeviceSynchronize();
+  if (e != cudaSuccess) { printf("  kernel error: %s\n", cudaGetErrorString(e)); exit(3); }
+  std::vector<int32_t> D(128 * N);
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  int bad = 0;
+  for (int r = 0; r < 128; ++r)
+    for (int n = 0; n < N; ++n) {
+      int32_t ref = 0;
+      for (int k = 0; k < K; ++k) ref += static_cast<int>(A[r * K + k]) * static_cast<int>(B[n * K + k]);
+      if (ref != D[r * N + n]) {
+        if (bad < 6 && verbose) printf("    D[%d][%d] = %d, want %d\n", r, n, D[r * N + n], ref);
+        ++bad;
+      }
+    }
+  printf("  mma mode=%s swap=%d N=%d K=%d a_signed=%d : %d / %d mismatches\n", mode ? "TS" : "SS", swap, N, K, a_signed, bad, 128 * N);
+  cudaFree(dA); cudaFree(dB); cudaFree(dAr); cudaFree(dD);
+  return bad;
+}
+
+// layout discovery when a hypothesis fails: B = "identity" rows so that D[r][n] = A[r][k = n]
+static void discover_ts() {
+  const int N = 64, K = 32;
+  std::vector<int8_t> A(128 * K), Bimg(N * K, 0), Aimg(128 * K, 0);
+  for (int r = 0; r < 128; ++r)
+    for (int k = 0; k < K; ++k) A[r * K + k] = static_cast<int8_t>(1 + k + 32 * (r % 3));
+  for (int n = 0; n < K; ++n) Bimg[core_off(n, n, K)] = 1;
+  int8_t *dA, *dB, *dAr; int32_t* dD;
+  CK(cudaMalloc(&dA, Aimg.size())); CK(cudaMalloc(&dB, Bimg.size())); CK(cudaMalloc(&dAr, A.size())); CK(cudaMalloc(&dD, 128 * N * 4));
+  CK(cudaMemcpy(dA, Aimg.data(), Aimg.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dB, Bimg.data(), Bimg.size(), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(dAr, A.data(), A.size(), cudaMemcpyHostToDevice));
+  probe_mma<<<1, 128, (128 + N) * K>>>(dA, dB, dAr, dD, 1, 0, N, K, 1);
+  CK(cudaDeviceSynchronize());
+  std::vector<int32_t> D(128 * N);
+  CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+  for (int r : {0, 1, 2, 33, 127}) {
+    printf("  discover TS row %3d (want 1+k+32*(r%%3)):", r);
+    for (int n = 0; n < 32; ++n) printf(" %d", D[r * N + n]);
+    printf("\n");
+  }
+  cudaFree(dA); cudaFree(dB); cudaFree(dAr); cudaFree(dD);
+}
+
+int main() {
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, 0));
+  printf("device: %s sm_%d%d, %d SMs\n", prop.name, prop.major, prop.minor, prop.multiProcessorCount);
+
+  printf("T1: SS mode\n");
+  int ss0 = run_mma_case(0, 0, 64, 128, 1, true);
+  int ss1 = run_mma_case(0, 1, 64, 128, 1, false);
+  printf("  => LBO/SBO hypothesis: %s\n", ss0 == 0 ? "as written (LBO = K-adjacent core matrices, SBO = 8-row groups)" : (ss1 == 0 ? "SWAPPED" : "NEITHER"));
+  const int swap = (ss0 != 0 && ss1 == 0) ? 1 : 0;
+  run_mma_case(0, swap, 128, 128, 1, true);
+  run_mma_case(0, swap, 256, 64, 1, true);
+  run_mma_case(0, swap, 64, 128, 0, true);   // unsigned A
+  run_mma_case(0, swap, 16, 32, 1, true);
+  printf("T2: TS mode (A in TMEM)\n");
+  int ts = run_mma_case(1, swap, 64, 128, 1, true);
+  run_mma_case(1, swap, 128, 128, 1, true);
+  run_mma_case(1, swap, 256, 32, 0, true);
+  if (ts != 0) discover_ts();
+
+  printf("T3: TMA\n");
+  EncodeTiledFn encode = get_encode();
+  {
+    const int n = 256 * 5 + 77;
+    std::vector<int32_t> h(n);
+    for (int i = 0; i < n; ++i) h[i] = i * 7 + 1;
+    int32_t *d, *o;
+    CK(cudaMalloc(&d, ((n * 4 + 15) / 16) * 16)); CK(cudaMalloc(&o, 1024 * 4));
+    CK(cudaMemcpy(d, h.data(), n * 4, cudaMemcpyHostToDevice));
+    CUtensorMap tm;
+    cuuint64_t gdim[1] = {static_cast<cuuint64_t>(n)};
+    cuuint64_t gstr[1] = {0};
+    cuuint32_t box[1] = {256};
+    cuuint32_t es[1] = {1};
+    CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_INT32, 1, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("  encode 1d: %d\n", static_cast<int>(r));
+    for (int c0 : {0, 36, 256 * 4 + 4, -8}) {
+      probe_tma1d<<<1, 128, 4 * 1024>>>(tm, c0, 2, o);
+      CK(cudaDeviceSynchronize());
+      std::vector<int32_t> got(512);
+      CK(cudaMemcpy(got.data(), o, 512 * 4, cudaMemcpyDeviceToHost));
+      int bad = 0;
+      for (int i = 0; i < 512; ++i) {
+        const int g = c0 + i;
+        const int32_t want = (g >= 0 && g < n) ? h[g] : 0;
+        if (got[i] != want) { if (bad < 4) printf("    1d c0=%d i=%d got %d want %d\n", c0, i, got[i], want); ++bad; }
+      }
+      printf("  tma 1d c0=%d: %d mismatches\n", c0, bad);
+    }
+    cudaFree(d); cudaFree(o);
+  }
+  {
+    const int R = 70, C = 64;   // 70 rows: the last box is partly out of bounds
+    std::vector<float> h(R * C);
+    for (int i = 0; i < R * C; ++i) h[i] = static_cast<float>(i);
+    float *d, *o, *raw;
+    CK(cudaMalloc(&d, R * C * 4)); CK(cudaMalloc(&o, R * C * 4)); CK(cudaMalloc(&raw, 4096));
+    CK(cudaMemcpy(d, h.data(), R * C * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemset(o, 0, R * C * 4));
+    CUtensorMap tmi, tmo;
+    cuuint64_t gdim[2] = {C, R};
+    cuuint64_t gstr[1] = {C * 4};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t es[2] = {1, 1};
+    CUresult r1 = encode(&tmi, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = encode(&tmo, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, o, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    printf("  encode 2d: %d %d\n", static_cast<int>(r1), static_cast<int>(r2));
+    for (int row0 : {0, 32, 64}) {
+      const int col0 = 32;
+      probe_tma2d<<<1, 128, 8192>>>(tmi, tmo, col0, row0, raw);
+      CK(cudaDeviceSynchronize());
+      std::vector<float> rw(1024), out(R * C);
+      CK(cudaMemcpy(rw.data(), raw, 4096, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(out.data(), o, R * C * 4, cudaMemcpyDeviceToHost));
+      int bad_sw = 0, bad_st = 0;
+      for (int r = 0; r < 32; ++r)
+        for (int c = 0; c < 32; ++c) {
+          const int phys = r * 32 + (((c >> 2) ^ (r & 7)) << 2) + (c & 3);
+          const float want = (row0 + r < R) ? h[(row0 + r) * C + col0 + c] : 0.f;
+          if (rw[phys] != want) { if (bad_sw < 4) printf("    swizzle r=%d c=%d got %g want %g\n", r, c, rw[phys], want); ++bad_sw; }
+          if (row0 + r < R && out[(row0 + r) * C + col0 + c] != 2.f * want) ++bad_st;
+        }
+      printf("  tma 2d row0=%d: swizzle-hypothesis mismatches %d, store mismatches %d\n", row0, bad_sw, bad_st);
+    }
+    cudaFree(d); cudaFree(o); cudaFree(raw);
+  }
+
+  printf("T4: MMA issue rate (148 CTAs, 1 per SM)\n");
+  {
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * 8));
+    CK(cudaFuncSetAttribute(probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int mode = 0; mode < 2; ++mode)
+      for (int N : {64, 128, 256}) {
+        const int iters = 8192;
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0); cudaEventCreate(&e1);
+        probe_rate<<<148, 128, (128 + 256) * 128>>>(mode, N, 64, dc);
+        CK(cudaDeviceSynchronize());
+        cudaEventRecord(e0);
+        probe_rate<<<148, 128, (128 + 256) * 128>>>(mode, N, iters, dc);
+        cudaEventRecord(e1);
+        CK(cudaDeviceSynchronize());
+        float ms;
+        cudaEventElapsedTime(&ms, e0, e1);
+        std::vector<long long> c(148);
+        CK(cudaMemcpy(c.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+        const double macs = 148.0 * iters * 128.0 * N * 32.0;
+        printf("  mode=%s N=%3d: %.3f ms, %.1f cycles/MMA (SM0), %.0f MAC/clk/SM, %.1f int8 TOP/s\n", mode ? "TS" : "SS", N, ms,
+               static_cast<double>(c[0]) / iters, 128.0 * N * 32.0 * iters / static_cast<double>(c[0]), 2.0 * macs / (ms * 1e-3) / 1e12);
+      }
+    cudaFree(dc);
+  }
+  printf("probe done\n");
+  return 0;
+}
