@@ -19,10 +19,12 @@
 #include "lce_b200.h"
 #include "lce_b200_kernels.cuh"
 #include "lce_b200_imma.cuh"
+#include "lce_b200_tc.cuh"
 
 namespace {
 thread_local std::string g_err;
 std::atomic<uint64_t> g_launches{0};
+std::atomic<uint64_t> g_path[3] = {};   // inner-product launches: tcgen05 / mma.sync / XOR + POPC
 }  // namespace
 
 // shared with lce_b200_builtins.cu
@@ -56,6 +58,8 @@ namespace {
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+// per-channel vectors (multiplier, bias, thresholds) are padded by one widest channel tile
+constexpr int kChanPad = 128;
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
 
 int grid_for(long long work_items, int per_block, int max_blocks = 148 * 16) {
@@ -125,11 +129,23 @@ struct GemmCore {
   int32_t* wpop = nullptr;      // popcount of each channel's filter row (padded by BN)
   int imma_Kc_v = 0, imma_chunks = 1;
   size_t imma_smem = 0;
+  // tcgen05 inner product (lce_b200_tc.cuh); absent when LCE_B200_BCONV_TC=0 or ineligible
+  bool tc_ok = false;
+  uint8_t* tc_wt = nullptr;        // [n_tiles][S_t][BN x 128 B] int8 stage images
+  int32_t* tc_wpop2 = nullptr;     // 2 * popcount of each filter row, padded
+  int32_t* tc_tap_popc_t = nullptr;  // [taps][ldc], zero-padding correction
+  int tc_BN = 0, tc_n_tiles = 0, tc_CcB = 0, tc_n_chunks = 1, tc_flat = 0, tc_V = 1;
+  int tc_S_full = 0, tc_S_last = 0, tc_S_t = 0, tc_ldc = 0;
+  // shape-dependent part, cached per input shape
+  long long tc_key_M = -1;
+  int tc_key_H = 0, tc_key_W = 0, tc_max_px = 0;
 
   void release() {
     cudaFree(wt); cudaFree(mul); cudaFree(bias); cudaFree(thr); cudaFree(tap_popc);
     cudaFree(wt_nat); cudaFree(wpop);
+    cudaFree(tc_wt); cudaFree(tc_wpop2); cudaFree(tc_tap_popc_t);
     wt = wt_nat = wpop = nullptr; mul = bias = nullptr; thr = tap_popc = nullptr;
+    tc_wt = nullptr; tc_wpop2 = tc_tap_popc_t = nullptr; tc_ok = false;
   }
 };
 
@@ -149,6 +165,7 @@ int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream
     attr_set = true;
   }
   lce::bconv_kernel<V, OUT><<<grid, lce::kThreads, smem, s>>>(p);
+  g_path[2].fetch_add(1, std::memory_order_relaxed);
   return launch_check("bconv_kernel");
 }
 size_t imma_smem_budget(int V) {
@@ -166,6 +183,7 @@ int launch_imma_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream
     attr_set = true;
   }
   lce::bconv_imma_kernel<V, OUT><<<grid, lce::kIThreads, smem, s>>>(p);
+  g_path[1].fetch_add(1, std::memory_order_relaxed);
   return launch_check("bconv_imma_kernel");
 }
 template <int V>
@@ -186,7 +204,9 @@ int launch_conv_v(int out_type, const lce::ConvKParams& p, dim3 grid, size_t sme
   }
   return fail("unsupported output type %d", out_type);
 }
-int launch_conv(const GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
+int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s);
+
+int launch_conv(GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
   p.fd_ohw = lce::make_fastdiv(static_cast<uint32_t>(p.OH) * p.OW);
   p.fd_ow = lce::make_fastdiv(p.OW);
   p.fd_cwv = lce::make_fastdiv(p.CwV);
@@ -197,6 +217,11 @@ int launch_conv(const GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
   const long long m_tiles = (p.M + lce::kBM - 1) / lce::kBM;
   if (m_tiles > INT_MAX) return fail("too many output pixels");
   if (p.img_words >= (1LL << 31)) return fail("input image too large (>= 2^31 packed words)");
+  if (c.tc_ok) {
+    // tcgen05 inner product: the same int32 accumulators again, persistent 128 x BN tiles
+    const int rc = tc_launch(c, p, s);
+    if (rc >= 0) return rc;
+  }
   if (c.wt_nat != nullptr && p.vec_store) {
     // int8 tensor-pipe inner product: 128 x 64 tiles, the same int32 accumulators as bconv_kernel
     lce::ConvKParams q = p;
@@ -218,6 +243,254 @@ int launch_conv(const GemmCore& c, lce::ConvKParams& p, cudaStream_t s) {
     case 4: return launch_conv_v<4>(c.out_type, p, grid, smem, s);
     case 2: return launch_conv_v<2>(c.out_type, p, grid, smem, s);
     default: return launch_conv_v<1>(c.out_type, p, grid, smem, s);
+  }
+}
+
+
+// ------------------------------------------------------------------------- //
+// tcgen05 path (lce_b200_tc.cuh): plan-time weight images and the launch.
+// ------------------------------------------------------------------------- //
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+EncodeTiledFn tensor_map_encoder() {
+  static EncodeTiledFn fn = [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess) {
+      cudaGetLastError();
+      f = nullptr;
+    }
+    return reinterpret_cast<EncodeTiledFn>(f);
+  }();
+  return fn;
+}
+int num_sms() {
+  static int n = [] {
+    int dev = 0, v = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    return v;
+  }();
+  return n;
+}
+constexpr size_t kTcSmemBudget = 226u * 1024u;   // dynamic shared memory of the one CTA per SM
+
+bool tc_enabled() {
+  const char* e = getenv("LCE_B200_BCONV_TC");  // read per plan: A/B in one process
+  return !(e && e[0] == '0');
+}
+
+// Weight stage images, 2 * popc(filter row) and the transposed tap popcounts. Eligibility that
+// does not depend on the input shape is decided here; the rest in tc_launch.
+int build_tc_weights(GemmCore* c, const int32_t* d_filter, bool want_tap_popc) {
+  c->tc_ok = false;
+  if (!tc_enabled() || c->groups != 1 || tensor_map_encoder() == nullptr) return 0;
+  if ((c->out_type == LCE_OUT_FLOAT || c->out_type == LCE_OUT_RAW_ACC) && (c->cout % 4 != 0 || c->cout < 32))
+    return 0;  // TMA store: 16-byte row pitch, 32-column boxes
+  if (want_tap_popc && c->taps > 64) return 0;
+  const int Cw = c->Cw_pg;
+  c->tc_BN = c->cout > 64 ? 128 : (c->cout > 32 ? 64 : 32);
+  c->tc_n_tiles = cdiv(c->cout, c->tc_BN);
+  if (Cw % 4 == 0) {
+    c->tc_flat = 0; c->tc_V = 4;
+    c->tc_CcB = std::min(Cw, 64);
+  } else {
+    c->tc_flat = 1; c->tc_V = (Cw % 2 == 0) ? 2 : 1;
+    c->tc_CcB = Cw;
+    if (Cw > 64) return 0;
+  }
+  c->tc_n_chunks = cdiv(Cw, c->tc_CcB);
+  const int cc_last = Cw - (c->tc_n_chunks - 1) * c->tc_CcB;
+  c->tc_S_full = cdiv(c->taps * c->tc_CcB, 4);
+  c->tc_S_last = cdiv(c->taps * cc_last, 4);
+  c->tc_S_t = (c->tc_n_chunks - 1) * c->tc_S_full + c->tc_S_last;
+  c->tc_ldc = c->tc_n_tiles * c->tc_BN;
+  const long long units = static_cast<long long>(c->tc_n_tiles) * c->tc_S_t * c->tc_BN * 4;
+  CUDA_OK(cudaMalloc(&c->tc_wt, static_cast<size_t>(units) * 32));
+  lce::tc::expand_weights_tc_kernel<<<grid_for(units, 256, 1 << 22), 256>>>(
+      d_filter, c->tc_wt, c->cout, c->taps, Cw, c->tc_CcB, c->tc_n_chunks, c->tc_BN, c->tc_S_full, c->tc_S_t, units);
+  if (launch_check("expand_weights_tc_kernel")) return 1;
+  CUDA_OK(cudaMalloc(&c->tc_wpop2, static_cast<size_t>(c->tc_ldc) * 4));
+  CUDA_OK(cudaMemset(c->tc_wpop2, 0, static_cast<size_t>(c->tc_ldc) * 4));
+  lce::tc::wpop2_kernel<<<cdiv(c->cout, 256), 256>>>(d_filter, c->tc_wpop2, c->cout, c->taps * Cw);
+  if (launch_check("wpop2_kernel")) return 1;
+  if (want_tap_popc) {
+    const size_t n = static_cast<size_t>(c->taps) * c->tc_ldc;
+    CUDA_OK(cudaMalloc(&c->tc_tap_popc_t, n * 4));
+    CUDA_OK(cudaMemset(c->tc_tap_popc_t, 0, n * 4));
+    lce::tc::tap_popc_t_kernel<<<cdiv(c->cout * c->taps, 256), 256>>>(d_filter, c->tc_tap_popc_t, c->cout, c->taps,
+                                                                       Cw, c->tc_ldc);
+    if (launch_check("tap_popc_t_kernel")) return 1;
+  }
+  c->tc_ok = true;
+  return 0;
+}
+
+// Largest halo (input pixels touched by one 128-pixel tile) over all tiles of this shape: the same
+// arithmetic as lce::tc::tile_halo, run once per (plan, input shape).
+int tc_max_halo_px(const lce::ConvKParams& p) {
+  long long best = 1;
+  const long long ohw = static_cast<long long>(p.OH) * p.OW;
+  const long long total_px = (p.M / ohw) * p.H * p.W;
+  auto flat = [&](long long m, int fy, int fx) {
+    const long long b = m / ohw, r = m - b * ohw;
+    const long long oy = r / p.OW, ox = r - oy * p.OW;
+    return (b * p.H + (oy * p.sh - p.ph + fy * p.dh)) * p.W + (ox * p.sw - p.pw + fx * p.dw);
+  };
+  for (long long m0 = 0; m0 < p.M; m0 += lce::tc::kBM) {
+    const long long m1 = std::min<long long>(m0 + lce::tc::kBM, p.M) - 1;
+    long long lo = std::max<long long>(flat(m0, 0, 0), 0);
+    const long long hi = std::min<long long>(flat(m1, p.KH - 1, p.KW - 1) + 1, total_px);
+    if (lo > total_px - 1) lo = total_px - 1;
+    best = std::max(best, std::max<long long>(hi - lo, 1));
+  }
+  return static_cast<int>(std::min<long long>(best, INT_MAX));
+}
+
+template <int V, int OUT>
+int launch_tc_vo(const CUtensorMap& tm_in, const CUtensorMap& tm_res, const CUtensorMap& tm_out,
+                 const lce::tc::TcParams& t, int grid, size_t smem, cudaStream_t s) {
+  static bool attr_set[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {  // the attribute is per device
+    CUDA_OK(cudaFuncSetAttribute(lce::tc::bconv_tc_kernel<V, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 static_cast<int>(kTcSmemBudget)));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
+  }
+  lce::tc::bconv_tc_kernel<V, OUT><<<grid, lce::tc::kThreads, smem, s>>>(tm_in, tm_res, tm_out, t);
+  g_path[0].fetch_add(1, std::memory_order_relaxed);
+  return launch_check("bconv_tc_kernel");
+}
+template <int V>
+int launch_tc_v(int out_type, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& c,
+                const lce::tc::TcParams& t, int grid, size_t smem, cudaStream_t s) {
+  switch (out_type) {
+    case LCE_OUT_FLOAT: return launch_tc_vo<V, LCE_OUT_FLOAT>(a, b, c, t, grid, smem, s);
+    case LCE_OUT_INT8: return launch_tc_vo<V, LCE_OUT_INT8>(a, b, c, t, grid, smem, s);
+    case LCE_OUT_BITPACKED: return launch_tc_vo<V, LCE_OUT_BITPACKED>(a, b, c, t, grid, smem, s);
+    default: return launch_tc_vo<V, LCE_OUT_RAW_ACC>(a, b, c, t, grid, smem, s);
+  }
+}
+
+// Returns -1 when this launch is not eligible (the caller falls through to the mma.sync / XOR
+// kernels), else the launch status.
+int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
+  namespace T = lce::tc;
+  if (!c.tc_ok || p.M >= (1LL << 31)) return -1;
+  const long long ohw = static_cast<long long>(p.OH) * p.OW;
+  const long long batch = p.M / ohw;
+  const long long total_px = batch * p.H * p.W;
+  const long long total_words = total_px * p.Cw_total;
+  if (total_words >= (1LL << 31) || total_px < 1) return -1;
+  if ((reinterpret_cast<uintptr_t>(p.in) & 15u) != 0) return -1;
+  const bool tma_out = c.out_type == LCE_OUT_FLOAT || c.out_type == LCE_OUT_RAW_ACC;
+  if (tma_out && (reinterpret_cast<uintptr_t>(p.out) & 15u) != 0) return -1;
+  if (p.residual != nullptr && (reinterpret_cast<uintptr_t>(p.residual) & 15u) != 0) return -1;
+  if (c.out_type == LCE_OUT_INT8 && (reinterpret_cast<uintptr_t>(p.out) & 15u) != 0) return -1;
+  if (c.tc_key_M != p.M || c.tc_key_H != p.H || c.tc_key_W != p.W) {
+    c.tc_max_px = tc_max_halo_px(p);
+    c.tc_key_M = p.M; c.tc_key_H = p.H; c.tc_key_W = p.W;
+  }
+  T::TcParams t;
+  memset(&t, 0, sizeof(t));
+  t.M = p.M; t.total_px = total_px;
+  t.H = p.H; t.W = p.W; t.OH = p.OH; t.OW = p.OW; t.KH = p.KH; t.KW = p.KW;
+  t.sh = p.sh; t.sw = p.sw; t.dh = p.dh; t.dw = p.dw; t.ph = p.ph; t.pw = p.pw;
+  t.taps = p.KH * p.KW;
+  t.Cw = c.Cw_pg; t.CcB = c.tc_CcB; t.n_chunks = c.tc_n_chunks; t.mode_flat = c.tc_flat;
+  t.cout = c.cout; t.BN = c.tc_BN; t.n_tiles = c.tc_n_tiles;
+  t.m_tiles = static_cast<int>((p.M + T::kBM - 1) / T::kBM);
+  t.S_full = c.tc_S_full; t.S_last = c.tc_S_last; t.S_t = c.tc_S_t;
+  // shared memory: weights | halo stages | epilogue slots | barriers
+  size_t raw_stage;
+  if (c.tc_flat) raw_stage = static_cast<size_t>(cdiv(c.tc_max_px * c.Cw_pg + 3, 256)) * 1024;
+  else raw_stage = static_cast<size_t>(cdiv(c.tc_max_px, 128)) * 128 * c.tc_CcB * 4;
+  raw_stage = (raw_stage + 1023) & ~size_t{1023};
+  t.raw_stage_bytes = static_cast<int>(raw_stage);
+  const size_t stage_bytes = static_cast<size_t>(c.tc_BN) * 128;
+  const bool has_res = p.residual != nullptr;
+  int nS = tma_out ? (has_res ? T::kMaxNS : 2) : 0;
+  const size_t fixed = T::kNR * raw_stage + T::kBarBytes;
+  if (fixed + 2 * T::kSlotBytes + 4 * stage_bytes > kTcSmemBudget) return -1;
+  auto stages_that_fit = [&](int ns) {
+    return static_cast<int>((kTcSmemBudget - fixed - static_cast<size_t>(ns) * T::kSlotBytes) / stage_bytes);
+  };
+  const bool can_reside = c.tc_n_tiles == 1 && c.tc_S_t <= T::kMaxNB;
+  if (can_reside && stages_that_fit(nS) < c.tc_S_t && has_res && stages_that_fit(2) >= c.tc_S_t) nS = 2;
+  int nB = std::min(stages_that_fit(nS), T::kMaxNB);
+  if (can_reside && nB >= c.tc_S_t) {
+    t.b_resident = 1;
+    nB = c.tc_S_t;
+  } else {
+    t.b_resident = 0;
+    if (nB < 4) return -1;
+    nB = std::min(nB, 12);  // a deeper ring buys nothing; leave the rest to L1
+  }
+  t.nB = nB; t.nS = nS;
+  t.off_raw = static_cast<int>(nB * stage_bytes);
+  t.off_slots = t.off_raw + T::kNR * t.raw_stage_bytes;
+  t.off_bar = t.off_slots + nS * T::kSlotBytes;
+  const size_t smem = static_cast<size_t>(t.off_bar) + T::kBarBytes;
+  t.clamp_min = p.clamp_min; t.clamp_max = p.clamp_max;
+  t.has_res = has_res ? 1 : 0; t.residual_act = p.residual_act;
+  t.cw_out = p.cw_out; t.zp_half = p.zp_half; t.ldc = c.tc_ldc;
+  t.wt = c.tc_wt; t.mul = p.mul; t.bias = p.bias; t.wpop2 = c.tc_wpop2; t.thr = p.thr;
+  t.tap_popc_t = p.tap_popc != nullptr ? c.tc_tap_popc_t : nullptr;
+  t.out = p.out; t.packed_out = p.packed_out;
+  t.fd_ohw = lce::make_fastdiv(static_cast<uint32_t>(ohw));
+  t.fd_ow = lce::make_fastdiv(p.OW);
+  t.fd_kw = lce::make_fastdiv(p.KW);
+  t.fd_cwv_full = lce::make_fastdiv(c.tc_CcB / c.tc_V);
+  t.fd_cwv_last = lce::make_fastdiv((c.Cw_pg - (c.tc_n_chunks - 1) * c.tc_CcB) / c.tc_V);
+  t.fd_mt = lce::make_fastdiv(t.m_tiles);
+
+  EncodeTiledFn enc = tensor_map_encoder();
+  CUtensorMap tm_in, tm_res, tm_out;
+  cuuint32_t es[2] = {1, 1};
+  if (c.tc_flat) {
+    cuuint64_t gd[1] = {static_cast<cuuint64_t>(total_words)};
+    cuuint64_t gs[1] = {0};
+    cuuint32_t box[1] = {256};
+    if (enc(&tm_in, CU_TENSOR_MAP_DATA_TYPE_INT32, 1, const_cast<int32_t*>(p.in), gd, gs, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (activations, flat) failed");
+  } else {
+    cuuint64_t gd[2] = {static_cast<cuuint64_t>(p.Cw_total), static_cast<cuuint64_t>(total_px)};
+    cuuint64_t gs[1] = {static_cast<cuuint64_t>(p.Cw_total) * 4};
+    cuuint32_t box[2] = {static_cast<cuuint32_t>(c.tc_CcB), 128};
+    if (enc(&tm_in, CU_TENSOR_MAP_DATA_TYPE_INT32, 2, const_cast<int32_t*>(p.in), gd, gs, box, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (activations) failed");
+  }
+  tm_res = tm_in;
+  tm_out = tm_in;
+  if (tma_out) {
+    cuuint64_t gd[2] = {static_cast<cuuint64_t>(c.cout), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t gs[1] = {static_cast<cuuint64_t>(c.cout) * 4};
+    cuuint32_t box_st[2] = {32, 32};
+    cuuint32_t box_ld[2] = {32, 128};
+    const CUtensorMapDataType dt =
+        c.out_type == LCE_OUT_FLOAT ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_INT32;
+    if (enc(&tm_out, dt, 2, p.out, gd, gs, box_st, es, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (output) failed");
+    if (has_res &&
+        enc(&tm_res, dt, 2, const_cast<float*>(p.residual), gd, gs, box_ld, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (shortcut) failed");
+  }
+  const long long items = static_cast<long long>(t.n_tiles) * t.m_tiles;
+  const int grid = static_cast<int>(std::min<long long>(items, num_sms()));
+  switch (c.tc_V) {
+    case 4: return launch_tc_v<4>(c.out_type, tm_in, tm_res, tm_out, t, grid, smem, s);
+    case 2: return launch_tc_v<2>(c.out_type, tm_in, tm_res, tm_out, t, grid, smem, s);
+    default: return launch_tc_v<1>(c.out_type, tm_in, tm_res, tm_out, t, grid, smem, s);
   }
 }
 
@@ -277,6 +550,7 @@ int build_core_weights(GemmCore* c, const int32_t* filter, bool want_tap_popc) {
     c->imma_smem = static_cast<size_t>(c->imma_Kc_v) * c->V * lce::kIBytesPerWord *
                    (c->imma_chunks > 1 ? 2 : 1);  // two-deep ring
   }
+  if (build_tc_weights(c, d_filter, want_tap_popc)) return 1;
   if (want_tap_popc) {
     const size_t n = static_cast<size_t>(c->cout + lce::kBN) * c->taps;
     CUDA_OK(cudaMalloc(&c->tap_popc, n * 4));
@@ -316,6 +590,20 @@ extern "C" {
 int lce_b200_abi_version(void) { return LCE_B200_ABI_VERSION; }
 const char* lce_b200_last_error(void) { return g_err.c_str(); }
 uint64_t lce_b200_launch_count(void) { return g_launches.load(); }
+void lce_b200_path_counts(uint64_t out[3]) {
+  for (int i = 0; i < 3; ++i) out[i] = g_path[i].load();
+}
+int lce_b200_tc_debug(int32_t out[8]) {
+  int flag = 0;
+  if (cudaMemcpyFromSymbol(&flag, lce::tc::g_tc_abort, sizeof(int)) != cudaSuccess) return 1;
+  if (cudaMemcpyFromSymbol(out, lce::tc::g_tc_dbg, 8 * sizeof(int)) != cudaSuccess) return 1;
+  out[7] = flag;
+  if (flag) {
+    const int zero = 0;
+    cudaMemcpyToSymbol(lce::tc::g_tc_abort, &zero, sizeof(int));
+  }
+  return 0;
+}
 
 int lce_b200_device_count(void) {
   int n = 0;
@@ -478,7 +766,7 @@ int lce_b200_bconv2d_create(const lce_bconv2d_desc* d, const int32_t* filter,
   c.out_type = d->out_type;
   int rc = build_core_weights(&c, filter, zero_pad);
 
-  const size_t padded = static_cast<size_t>(c.cout) + lce::kBN;
+  const size_t padded = static_cast<size_t>(c.cout) + kChanPad;
   if (!rc && d->out_type != LCE_OUT_BITPACKED) {
     // OneTimeSetup (bconv2d.cc:353-389): fold in double on the host.
     std::vector<float> pm(c.cout), pb(c.cout), fm(padded, 0.f), fb(padded, 0.f);
@@ -554,7 +842,7 @@ static int bconv_run_impl(lce_b200_bconv2d* plan, const int32_t* in_dev, void* o
                           const float* residual, int residual_act, int32_t* packed_out,
                           void* stream) {
   const lce_bconv2d_desc& d = plan->d;
-  const GemmCore& c = plan->core;
+  GemmCore& c = plan->core;
   cudaStream_t s = as_stream(stream);
   lce::ConvKParams p;
   memset(&p, 0, sizeof(p));
@@ -685,7 +973,7 @@ int lce_b200_bgemm_create(int N, int Kw, const int32_t* W, const lce_bgemm_epilo
   c.out_type = ep->out_type;
   c.clamp_min = ep->clamp_min; c.clamp_max = ep->clamp_max;
   int rc = build_core_weights(&c, W, false);
-  const size_t padded = static_cast<size_t>(N) + lce::kBN;
+  const size_t padded = static_cast<size_t>(N) + kChanPad;
   if (!rc && (ep->out_type == LCE_OUT_FLOAT || ep->out_type == LCE_OUT_INT8)) {
     if (!ep->multiplier || !ep->bias) rc = fail("bgemm: multiplier/bias missing");
     void *dm = nullptr, *db = nullptr;
@@ -710,7 +998,7 @@ int lce_b200_bgemm_create(int N, int Kw, const int32_t* W, const lce_bgemm_epilo
 
 int lce_b200_bgemm_run(lce_b200_bgemm* plan, int64_t M, const int32_t* A_dev, void* out_dev,
                        void* stream) {
-  const GemmCore& c = plan->core;
+  GemmCore& c = plan->core;
   if (M < 0) return fail("bgemm: negative M");
   if (M == 0) return 0;
   if (M > INT_MAX) return fail("bgemm: M too large");

@@ -1,0 +1,657 @@
+// lce_b200_tc.cuh -- the binary convolution / BGEMM on the 5th-generation tensor cores.
+//
+//   acc[m][n] = sum_k popc(a[m][k] ^ w[n][k]) = popc(w[n]) + sum_k a_k * w'_k
+//   a_k in {0,1},  w'_k = +1 if w_k = 0 else -1            (same identity as lce_b200_imma.cuh)
+//
+// so the reference's integers (LCE/core/bconv2d/reference.h:35-148, bgemm/kernels.h:22-134) come
+// out of one int8 contraction, issued here as tcgen05.mma kind::i8 (SASS UTCIMMA) with the
+// accumulators in TMEM. HBM, L2 and the TMA-staged activation tiles keep the reference's BITPACKED
+// words (types.h:41-47); bytes exist only in TMEM (activations) and in a plan-time expansion of
+// the static weights.
+//
+// One persistent CTA per SM, 16 warps, warp-specialised:
+//   w0        activation producer  TMA (cp.async.bulk.tensor, SASS UTMALDG) of the packed HALO
+//                                  of a 128-pixel tile: the contiguous pixel range its taps touch,
+//                                  once per tile -- no im2col replication anywhere
+//   w1        MMA issuer           one lane issues tcgen05.mma.cta_group::1.kind::i8, A from TMEM,
+//                                  B from shared memory, D (128 x BN int32) in TMEM, two D buffers
+//   w2        weight producer      cp.async.bulk of pre-expanded int8 stages (resident in shared
+//                                  memory for the whole kernel when they fit, else a ring)
+//   w3        shortcut producer    TMA tiles of the residual (fused ADD), SWIZZLE_128B
+//   w4..w11   expanders            thread = output pixel = TMEM lane: reads its taps' words from
+//                                  the halo (out-of-bounds taps read as 0 = "+1" padding,
+//                                  reference.h:106), expands bits -> bytes (9 ALU ops per word:
+//                                  bit 8i+s of a word becomes byte i of column s with VALUE
+//                                  2^(s&3); the weight byte there is +-(8 >> (s&3)), so every
+//                                  product is +-8 and D holds 8 * sum a*w') and writes them with
+//                                  tcgen05.st; two warps per TMEM lane quadrant take alternate stages
+//   w12..w15  epilogue             tcgen05.ld -> OutputTransform (output_transform.h:94-168,
+//                                  unfused fmul + fadd) [+ shortcut, activation, next layer's sign
+//                                  bits] -> swizzled shared memory -> TMA store (UTMASTG)
+// Stage = 4 K-words = 128 bits of K = four K=32 MMAs; 8 A stages live in TMEM columns 256..511.
+#ifndef LCE_B200_TC_CUH_
+#define LCE_B200_TC_CUH_
+
+#include <cuda.h>
+
+#include "lce_b200_kernels.cuh"
+
+namespace lce {
+namespace tc {
+
+constexpr int kBM = 128;
+constexpr int kThreads = 512;
+constexpr int kNA = 8;            // A stages in TMEM, 32 columns each
+constexpr int kNR = 2;            // activation-halo stages
+constexpr int kMaxNB = 32;        // weight stages in shared memory (barrier array size)
+constexpr int kMaxNS = 4;         // epilogue staging slots
+constexpr int kSlotBytes = kBM * 128;  // 128 rows x 32 columns x 4 B
+constexpr int kFirstExpWarp = 4, kNumExpWarps = 8, kFirstEpiWarp = 12;
+constexpr int kBarBytes = 1024;
+
+struct TcParams {
+  long long M;           // output pixels (< 2^31)
+  long long total_px;    // input pixels batch * H * W
+  int H, W, OH, OW, KH, KW, sh, sw, dh, dw, ph, pw;
+  int taps;
+  int Cw;                // channel words per pixel
+  int CcB;               // words per pixel in a halo stage (box width; == Cw in flat mode)
+  int n_chunks;          // channel chunks of CcB words
+  int mode_flat;         // 1: 1-D word map, boxes of 256 words; 0: 2-D [pixel][word] map, boxes of CcB x 128
+  int cout, BN, n_tiles, m_tiles;
+  int S_full, S_last, S_t;   // weight stages per full / last chunk, per tile
+  int nB, b_resident, nS;
+  int raw_stage_bytes;
+  int off_raw, off_slots, off_bar;   // byte offsets in dynamic shared memory (weights at 0)
+  int clamp_min, clamp_max;
+  int has_res, residual_act, cw_out, zp_half, ldc;   // ldc: padded channel count of the tables
+  const uint8_t* wt;       // [n_tiles][S_t][BN x 128 B core-matrix image]
+  const float* mul;        // folded multiplier / bias, padded to n_tiles * BN
+  const float* bias;
+  const int32_t* wpop2;    // 2 * popcount of each channel's filter row
+  const int32_t* thr;
+  const int32_t* tap_popc_t;  // [taps][ldc] or nullptr (zero-padding correction)
+  void* out;
+  int32_t* packed_out;
+  FastDiv fd_ohw, fd_ow, fd_kw, fd_cwv_full, fd_cwv_last, fd_mt;
+};
+
+// ------------------------------------------------------------------ PTX
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// Deadlock watchdog (development aid, costs one counter per wait): a wait that does not complete
+// within ~2 s records who was waiting on what in g_tc_dbg, raises g_tc_abort, and every later wait
+// returns at once so the kernel terminates and the host can read the record (lce_b200_tc_debug).
+__device__ int g_tc_abort = 0;
+__device__ int g_tc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+__device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+__device__ __noinline__ void tc_watchdog_fire(int tag, uint32_t parity, uint32_t cnt) {
+  if (atomicCAS(&g_tc_abort, 0, 1) == 0) {
+    g_tc_dbg[0] = tag; g_tc_dbg[1] = static_cast<int>(blockIdx.x); g_tc_dbg[2] = static_cast<int>(threadIdx.x);
+    g_tc_dbg[3] = static_cast<int>(parity); g_tc_dbg[4] = static_cast<int>(cnt);
+  }
+}
+__device__ __forceinline__ void mbar_wait_tc(uint64_t* bar, uint32_t parity, int tag = 0, uint32_t cnt = 0) {
+  if (mbar_try(bar, parity)) return;
+  const long long t0 = clock64();
+  for (uint32_t i = 1;; ++i) {
+    if (mbar_try(bar, parity)) return;
+    if ((i & 255u) == 0) {
+      if (*reinterpret_cast<volatile int*>(&g_tc_abort) != 0) return;
+      if (clock64() - t0 > 4000000000LL) {
+        tc_watchdog_fire(tag, parity, cnt);
+        return;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], int8 x int8 -> int32, M = 128
+__device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
+}
+// K-major, no swizzle: 8 x 16 B core matrices, K-adjacent ones 128 B apart (LBO), 8-row groups
+// 1024 B apart (SBO); descriptor version 1 (Blackwell). Verified on hardware by tools/tc_probe.cu.
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
+  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(128 >> 4) << 16) |
+         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46);
+}
+// kind::i8 instruction descriptor: D = s32, A = B = s8, both K-major, M = 128
+__host__ __device__ inline uint32_t make_idesc(int N) {
+  return (2u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(kBM >> 4) << 24);
+}
+#define LCE_R8(a, o) "%" #a "+" #o
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+      "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+      "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+      "r"(r[31])
+      : "memory");
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0) {
+  asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0) : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(reinterpret_cast<uint64_t>(tm)),
+               "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// ------------------------------------------------------------------ index helpers
+struct Pixel { int b, oy, ox; };
+__device__ __forceinline__ Pixel split_px(const TcParams& p, uint32_t m) {
+  Pixel r;
+  const uint32_t bb = fdiv(m, p.fd_ohw);
+  const uint32_t rem = m - bb * static_cast<uint32_t>(p.OH * p.OW);
+  const uint32_t y = fdiv(rem, p.fd_ow);
+  r.b = static_cast<int>(bb);
+  r.oy = static_cast<int>(y);
+  r.ox = static_cast<int>(rem - y * static_cast<uint32_t>(p.OW));
+  return r;
+}
+// The contiguous range of input pixels (flattened (b, y, x)) that the taps of tile m0 touch. The
+// flattened index of (pixel m, tap) grows with m and with the tap, so the range runs from the first
+// pixel's first tap to the last pixel's last tap, clipped to the tensor.
+__device__ __forceinline__ void tile_halo(const TcParams& p, long long m0, long long* px_lo, int* px_cnt) {
+  const long long m1 = min(m0 + kBM, p.M) - 1;
+  const Pixel a = split_px(p, static_cast<uint32_t>(m0));
+  const Pixel z = split_px(p, static_cast<uint32_t>(m1));
+  long long lo = (static_cast<long long>(a.b) * p.H + (a.oy * p.sh - p.ph)) * p.W + (a.ox * p.sw - p.pw);
+  long long hi = (static_cast<long long>(z.b) * p.H + (z.oy * p.sh - p.ph + (p.KH - 1) * p.dh)) * p.W +
+                 (z.ox * p.sw - p.pw + (p.KW - 1) * p.dw) + 1;
+  lo = max(lo, 0LL);
+  hi = min(hi, p.total_px);
+  if (lo > p.total_px - 1) lo = p.total_px - 1;
+  *px_lo = lo;
+  *px_cnt = static_cast<int>(max(hi - lo, 1LL));
+}
+// first word held by the halo stage (the TMA start coordinate must be 16-byte aligned: tools/tc_probe.cu)
+__device__ __forceinline__ long long halo_word_base(const TcParams& p, long long px_lo) {
+  return p.mode_flat ? ((px_lo * p.Cw) & ~3LL) : px_lo * p.CcB;
+}
+
+// bit 8i+s of w -> byte i of v[s], value 2^(s&3): 9 ALU instructions
+__device__ __forceinline__ void expand_word(uint32_t w, uint32_t* v) {
+  v[0] = w & 0x01010101u; v[1] = w & 0x02020202u; v[2] = w & 0x04040404u; v[3] = w & 0x08080808u;
+  const uint32_t h = w >> 4;
+  v[4] = h & 0x01010101u; v[5] = h & 0x02020202u; v[6] = h & 0x04040404u; v[7] = h & 0x08080808u;
+}
+
+// Plan time: the weights of one (n tile, stage) as the exact shared-memory image the MMA reads:
+// [BN rows][128 B], no-swizzle K-major core matrices. Stage order = (channel chunk, tap, word).
+// One thread per (n tile, stage, row, word) writes that word's 32 bytes.
+__global__ void expand_weights_tc_kernel(const int32_t* __restrict__ filter, uint8_t* __restrict__ wt, int cout, int taps,
+                                         int Cw, int CcB, int n_chunks, int BN, int S_full, int S_t, long long total) {
+  const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+  if (idx >= total) return;
+  const int j = static_cast<int>(idx & 3);
+  long long r = idx >> 2;
+  const int n = static_cast<int>(r % BN);
+  r /= BN;
+  const int st = static_cast<int>(r % S_t);
+  const int nt = static_cast<int>(r / S_t);
+  int chunk = st / S_full;
+  if (chunk > n_chunks - 1) chunk = n_chunks - 1;
+  const int sic = st - chunk * S_full;
+  const int cc_this = min(CcB, Cw - chunk * CcB);
+  const int q = sic * 4 + j;
+  const int c = nt * BN + n;
+  uint32_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (q < taps * cc_this && c < cout) {
+    const int tap = q / cc_this, cwi = q - tap * cc_this;
+    const uint32_t w = static_cast<uint32_t>(filter[(static_cast<long long>(c) * taps + tap) * Cw + chunk * CcB + cwi]);
+    for (int kk = 0; kk < 32; ++kk) {
+      const int s = kk >> 2, i = kk & 3;
+      const int mag = 8 >> (s & 3);
+      const int v = ((w >> (8 * i + s)) & 1u) ? -mag : mag;
+      bytes[kk >> 2] |= (static_cast<uint32_t>(v) & 0xFFu) << (8 * (kk & 3));
+    }
+  }
+  uint8_t* dst = wt + (static_cast<long long>(nt) * S_t + st) * BN * 128 + (n >> 3) * 1024 + (2 * j) * 128 + (n & 7) * 16;
+  *reinterpret_cast<uint4*>(dst) = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
+  *reinterpret_cast<uint4*>(dst + 128) = make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]);
+}
+// tap_popc_t[t][c] = popcount of filter[c][t][:] (transposed for the epilogue's per-pixel rows)
+__global__ void tap_popc_t_kernel(const int32_t* __restrict__ filter, int32_t* __restrict__ out, int cout, int taps, int Cw,
+                                  int ldc) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= cout * taps) return;
+  const int c = idx / taps, t = idx - c * taps;
+  const int32_t* f = filter + static_cast<size_t>(idx) * Cw;
+  int s = 0;
+  for (int w = 0; w < Cw; ++w) s += __popc(static_cast<uint32_t>(f[w]));
+  out[static_cast<size_t>(t) * ldc + c] = s;
+}
+__global__ void wpop2_kernel(const int32_t* __restrict__ filter, int32_t* __restrict__ out, int cout, int Kw) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cout) return;
+  const int32_t* f = filter + static_cast<size_t>(c) * Kw;
+  int s = 0;
+  for (int w = 0; w < Kw; ++w) s += __popc(static_cast<uint32_t>(f[w]));
+  out[c] = 2 * s;
+}
+
+// ------------------------------------------------------------------ the kernel
+template <int V, int OUT>
+__global__ void __launch_bounds__(kThreads, 1)
+bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant__ CUtensorMap tm_res,
+                const __grid_constant__ CUtensorMap tm_out, const TcParams p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.off_bar);
+  uint32_t* tmem_base_p = reinterpret_cast<uint32_t*>(smem + p.off_bar + kBarBytes - 16);
+  uint64_t* b_full = bars;                     // [kMaxNB]
+  uint64_t* b_empty = b_full + kMaxNB;         // [kMaxNB]
+  uint64_t* raw_full = b_empty + kMaxNB;       // [kNR]
+  uint64_t* raw_empty = raw_full + kNR;        // [kNR]
+  uint64_t* a_full = raw_empty + kNR;          // [kNA]
+  uint64_t* a_empty = a_full + kNA;            // [kNA]
+  uint64_t* d_full = a_empty + kNA;            // [2]
+  uint64_t* d_empty = d_full + 2;              // [2]
+  uint64_t* res_full = d_empty + 2;            // [kMaxNS]
+  uint64_t* res_empty = res_full + kMaxNS;     // [kMaxNS]
+
+  const int tid = threadIdx.x;
+  const int warp = tid >> 5, lane = tid & 31;
+
+  if (tid == 0) {
+    for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < kNR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kNumExpWarps); }
+    for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+    for (int i = 0; i < kMaxNS; ++i) { mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_base_p, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_base_p;
+  const uint32_t tmem_a = tmem + 256;
+
+  const int n_items = p.n_tiles * p.m_tiles;
+  const int cwv_full = p.CcB / V;
+  const int cwv_last = (p.Cw - (p.n_chunks - 1) * p.CcB) / V;
+  constexpr int VPS = 4 / V;   // vectors per stage
+
+  if (warp == 0) {
+    // ===== activation producer =====
+    if (lane == 0) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
+        const long long m0 = static_cast<long long>(item - nt * p.m_tiles) * kBM;
+        long long px_lo;
+        int px_cnt;
+        tile_halo(p, m0, &px_lo, &px_cnt);
+        const long long wbase = halo_word_base(p, px_lo);
+        for (int ch = 0; ch < p.n_chunks; ++ch, ++cnt) {
+          const int rs = cnt % kNR;
+          mbar_wait_tc(&raw_empty[rs], ((cnt / kNR) & 1) ^ 1, 1);
+          unsigned char* dst = smem + p.off_raw + rs * p.raw_stage_bytes;
+          if (p.mode_flat) {
+            const int nwords = static_cast<int>((px_lo + px_cnt) * p.Cw - wbase);
+            const int nbox = (nwords + 255) >> 8;
+            mbar_arrive_expect_tx(&raw_full[rs], nbox * 1024);
+            for (int i = 0; i < nbox; ++i) tma_load_1d(dst + i * 1024, &tm_in, &raw_full[rs], static_cast<int>(wbase) + i * 256);
+          } else {
+            const int nbox = (px_cnt + 127) >> 7;
+            const int box_bytes = 128 * p.CcB * 4;
+            mbar_arrive_expect_tx(&raw_full[rs], nbox * box_bytes);
+            for (int i = 0; i < nbox; ++i)
+              tma_load_2d(dst + i * box_bytes, &tm_in, &raw_full[rs], ch * p.CcB, static_cast<int>(px_lo) + i * 128);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc(p.BN);
+      const uint32_t stage_bytes = p.BN * 128;
+      uint32_t cntA = 0, cntB = 0, it = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+        const uint32_t ds = it & 1;
+        mbar_wait_tc(&d_empty[ds], ((it >> 1) & 1) ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_addr = tmem + ds * p.BN;
+        uint32_t first = 1;
+        int st_tile = 0;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          const int nq = p.taps * (ch == p.n_chunks - 1 ? p.Cw - ch * p.CcB : p.CcB);
+          const int nst = (nq + 3) >> 2;
+          for (int st = 0; st < nst; ++st, ++cntA, ++st_tile) {
+            const int as = cntA % kNA;
+            uint32_t bs;
+            if (p.b_resident) {
+              bs = st_tile;
+              mbar_wait_tc(&b_full[bs], 0, 3);
+            } else {
+              bs = cntB % p.nB;
+              mbar_wait_tc(&b_full[bs], (cntB / p.nB) & 1, 3);
+            }
+            mbar_wait_tc(&a_full[as], (cntA / kNA) & 1, 4);
+            tc_fence_after();
+            const int nw = min(4, nq - st * 4);
+            const uint32_t b_addr = smem_u32(smem) + bs * stage_bytes;
+            for (int j = 0; j < nw; ++j) {
+              mma_i8_ts(d_addr, tmem_a + as * 32 + j * 8, make_bdesc(b_addr + j * 256), idesc, first ? 0u : 1u);
+              first = 0;
+            }
+            tc_commit(&a_empty[as]);
+            if (!p.b_resident) {
+              tc_commit(&b_empty[bs]);
+              ++cntB;
+            }
+          }
+        }
+        tc_commit(&d_full[ds]);
+      }
+    }
+  } else if (warp == 2) {
+    // ===== weight producer =====
+    if (lane == 0) {
+      const uint32_t stage_bytes = p.BN * 128;
+      if (p.b_resident) {
+        if (blockIdx.x < n_items) {
+          for (int st = 0; st < p.S_t; ++st) {
+            mbar_arrive_expect_tx(&b_full[st], stage_bytes);
+            bulk_g2s(smem + st * stage_bytes, p.wt + static_cast<size_t>(st) * stage_bytes, stage_bytes, &b_full[st]);
+          }
+        }
+      } else {
+        uint32_t cnt = 0;
+        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+          const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
+          const uint8_t* src = p.wt + static_cast<size_t>(nt) * p.S_t * stage_bytes;
+          for (int st = 0; st < p.S_t; ++st, ++cnt) {
+            const int bs = cnt % p.nB;
+            mbar_wait_tc(&b_empty[bs], ((cnt / p.nB) & 1) ^ 1, 5);
+            mbar_arrive_expect_tx(&b_full[bs], stage_bytes);
+            bulk_g2s(smem + bs * stage_bytes, src + static_cast<size_t>(st) * stage_bytes, stage_bytes, &b_full[bs]);
+          }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ===== shortcut producer =====
+    if (lane == 0 && p.has_res) {
+      uint32_t cnt = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
+        const long long m0 = static_cast<long long>(item - nt * p.m_tiles) * kBM;
+        const int c_tile = nt * p.BN;
+        const int n_cc = min(p.BN, p.cout - c_tile + 31) >> 5;
+        for (int cc = 0; cc < n_cc; ++cc, ++cnt) {
+          const int sl = cnt % p.nS;
+          mbar_wait_tc(&res_empty[sl], ((cnt / p.nS) & 1) ^ 1, 6);
+          mbar_arrive_expect_tx(&res_full[sl], kSlotBytes);
+          tma_load_2d(smem + p.off_slots + sl * kSlotBytes, &tm_res, &res_full[sl], c_tile + cc * 32, static_cast<int>(m0));
+        }
+      }
+    }
+  } else if (warp < kFirstEpiWarp) {
+    // ===== expanders: thread = output pixel = TMEM lane =====
+    const int q = warp & 3;
+    const int group = (warp - kFirstExpWarp) >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    uint32_t cntA = 0, cntR = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+      const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
+      const long long m0 = static_cast<long long>(item - nt * p.m_tiles) * kBM;
+      long long px_lo;
+      int px_cnt;
+      tile_halo(p, m0, &px_lo, &px_cnt);
+      const long long wbase = halo_word_base(p, px_lo);
+      const long long m = m0 + row;
+      const bool row_ok = m < p.M;
+      int iy0 = 0, ix0 = 0, off0 = 0;
+      const int pitch = p.mode_flat ? p.Cw : p.CcB;
+      if (row_ok) {
+        const Pixel px = split_px(p, static_cast<uint32_t>(m));
+        iy0 = px.oy * p.sh - p.ph;
+        ix0 = px.ox * p.sw - p.pw;
+        // word offset of (this pixel's tap (0,0), channel word 0) inside the halo stage
+        off0 = static_cast<int>(((static_cast<long long>(px.b) * p.H + iy0) * p.W + ix0) * pitch - wbase);
+      }
+      for (int ch = 0; ch < p.n_chunks; ++ch, ++cntR) {
+        const int rs = cntR % kNR;
+        const bool last = ch == p.n_chunks - 1;
+        const int cwv = last ? cwv_last : cwv_full;
+        const FastDiv fd_cwv = last ? p.fd_cwv_last : p.fd_cwv_full;
+        const int nvec = p.taps * cwv;
+        const int nst = (nvec + VPS - 1) / VPS;
+        const uint32_t* raw = reinterpret_cast<const uint32_t*>(smem + p.off_raw + rs * p.raw_stage_bytes);
+        mbar_wait_tc(&raw_full[rs], (cntR / kNR) & 1, 7);
+        for (int st = 0; st < nst; ++st, ++cntA) {
+          if ((cntA & 1) != static_cast<uint32_t>(group)) continue;
+          const int as = cntA % kNA;
+          uint32_t v[32];
+          int kv = st * VPS;
+          int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kv), fd_cwv));
+          int cv = kv - tap * cwv;
+          int fy = static_cast<int>(fdiv(static_cast<uint32_t>(tap), p.fd_kw));
+          int fx = tap - fy * p.KW;
+#pragma unroll
+          for (int u = 0; u < VPS; ++u) {
+            uint32_t w[V];
+#pragma unroll
+            for (int e = 0; e < V; ++e) w[e] = 0;
+            const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
+            if (row_ok && kv + u < nvec && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
+                static_cast<unsigned>(ix) < static_cast<unsigned>(p.W))
+              load_words<V>(reinterpret_cast<const typename VecT<V>::T*>(raw + off0 + (fy * p.dh * p.W + fx * p.dw) * pitch + cv * V), w);
+#pragma unroll
+            for (int e = 0; e < V; ++e) expand_word(w[e], &v[(u * V + e) * 8]);
+            if (++cv == cwv) {
+              cv = 0;
+              if (++fx == p.KW) { fx = 0; ++fy; }
+            }
+          }
+          mbar_wait_tc(&a_empty[as], ((cntA / kNA) & 1) ^ 1, 8);
+          tc_fence_after();
+          tmem_st32(tmem_a + lane_base + as * 32, v);
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_full[as]);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&raw_empty[rs]);
+      }
+    }
+  } else {
+    // ===== epilogue: thread = output pixel = TMEM lane =====
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const float act_lo = p.residual_act == LCE_ACT_RELU_N1_TO_1 ? -1.0f : 0.0f;
+    const float act_hi = p.residual_act == LCE_ACT_RELU ? __int_as_float(0x7f800000)
+                                                        : (p.residual_act == LCE_ACT_RELU6 ? 6.0f : 1.0f);
+    uint32_t it = 0, cntS = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
+      const long long m0 = static_cast<long long>(item - nt * p.m_tiles) * kBM;
+      const int c_tile = nt * p.BN;
+      const int n_cc = min(p.BN, p.cout - c_tile + 31) >> 5;
+      const long long m = m0 + row;
+      const bool row_ok = m < p.M;
+      const uint32_t ds = it & 1;
+      // zero-padding: which taps of this pixel fall outside the image (reference.h:100-103)
+      unsigned long long oob = 0;
+      if (p.tap_popc_t != nullptr && row_ok) {
+        const Pixel px = split_px(p, static_cast<uint32_t>(m));
+        const int iy0 = px.oy * p.sh - p.ph, ix0 = px.ox * p.sw - p.pw;
+        for (int fy = 0; fy < p.KH; ++fy)
+          for (int fx = 0; fx < p.KW; ++fx) {
+            const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
+            if (!(static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)))
+              oob |= 1ull << (fy * p.KW + fx);
+          }
+      }
+      mbar_wait_tc(&d_full[ds], (it >> 1) & 1, 9);
+      tc_fence_after();
+      for (int cc = 0; cc < n_cc; ++cc) {
+        uint32_t accu[32];
+        tmem_ld32(tmem + lane_base + ds * p.BN + cc * 32, accu);
+        if (cc == n_cc - 1) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&d_empty[ds]);
+        }
+        const int c0 = c_tile + cc * 32;
+        // x = 2 * acc = (acc8 >> 2) + 2 * popc(w)   (acc8 is a multiple of 8)
+        int x[32];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const int4 wp = __ldg(reinterpret_cast<const int4*>(p.wpop2 + c0) + k);
+          x[4 * k] = (static_cast<int>(accu[4 * k]) >> 2) + wp.x;
+          x[4 * k + 1] = (static_cast<int>(accu[4 * k + 1]) >> 2) + wp.y;
+          x[4 * k + 2] = (static_cast<int>(accu[4 * k + 2]) >> 2) + wp.z;
+          x[4 * k + 3] = (static_cast<int>(accu[4 * k + 3]) >> 2) + wp.w;
+        }
+        if (oob != 0) {
+          for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
+            const int t = __ffsll(static_cast<long long>(mk)) - 1;
+            const int4* tp = reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const int4 tv = __ldg(tp + k);
+              x[4 * k] += 2 * (p.zp_half - tv.x);
+              x[4 * k + 1] += 2 * (p.zp_half - tv.y);
+              x[4 * k + 2] += 2 * (p.zp_half - tv.z);
+              x[4 * k + 3] += 2 * (p.zp_half - tv.w);
+            }
+          }
+        }
+        if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_RAW_ACC) {
+          const int sl = cntS % p.nS;
+          unsigned char* buf = smem + p.off_slots + sl * kSlotBytes + q * 4096 + lane * 128;
+          if (OUT == LCE_OUT_FLOAT && p.has_res) mbar_wait_tc(&res_full[sl], (cntS / p.nS) & 1, 10);
+          uint32_t bits = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            uint4* cell = reinterpret_cast<uint4*>(buf + ((k ^ (lane & 7)) << 4));
+            if (OUT == LCE_OUT_RAW_ACC) {
+              *cell = make_uint4(x[4 * k] >> 1, x[4 * k + 1] >> 1, x[4 * k + 2] >> 1, x[4 * k + 3] >> 1);
+            } else {
+              const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mul + c0) + k);
+              const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + k);
+              float y0 = transform_float_x2(x[4 * k], p.clamp_min, p.clamp_max, mu.x, bi.x);
+              float y1 = transform_float_x2(x[4 * k + 1], p.clamp_min, p.clamp_max, mu.y, bi.y);
+              float y2 = transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z);
+              float y3 = transform_float_x2(x[4 * k + 3], p.clamp_min, p.clamp_max, mu.w, bi.w);
+              if (p.has_res) {
+                const float4 rv = *reinterpret_cast<const float4*>(cell);
+                y0 = __fadd_rn(y0, rv.x); y1 = __fadd_rn(y1, rv.y); y2 = __fadd_rn(y2, rv.z); y3 = __fadd_rn(y3, rv.w);
+                if (p.residual_act != LCE_ACT_NONE) {
+                  y0 = fminf(fmaxf(y0, act_lo), act_hi); y1 = fminf(fmaxf(y1, act_lo), act_hi);
+                  y2 = fminf(fmaxf(y2, act_lo), act_hi); y3 = fminf(fmaxf(y3, act_lo), act_hi);
+                }
+              }
+              *reinterpret_cast<float4*>(cell) = make_float4(y0, y1, y2, y3);
+              bits |= ((y0 < 0.0f ? 1u : 0u) | (y1 < 0.0f ? 2u : 0u) | (y2 < 0.0f ? 4u : 0u) | (y3 < 0.0f ? 8u : 0u)) << (4 * k);
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            if (m0 + q * 32 < p.M) {
+              tma_store_2d(&tm_out, smem + p.off_slots + sl * kSlotBytes + q * 4096, c0, static_cast<int>(m0) + q * 32);
+              tma_store_wait_read();
+            }
+            if (OUT == LCE_OUT_FLOAT && p.has_res) mbar_arrive(&res_empty[sl]);
+          }
+          __syncwarp();
+          if (OUT == LCE_OUT_FLOAT && p.packed_out != nullptr && row_ok)
+            p.packed_out[static_cast<size_t>(m) * p.cw_out + (c0 >> 5)] = static_cast<int32_t>(bits);
+          ++cntS;
+        } else if (OUT == LCE_OUT_INT8) {
+          if (row_ok) {
+            uint32_t pk[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) {
+              const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mul + c0) + k);
+              const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + k);
+              const int q0 = round_saturate_i8(transform_float_x2(x[4 * k], p.clamp_min, p.clamp_max, mu.x, bi.x));
+              const int q1 = round_saturate_i8(transform_float_x2(x[4 * k + 1], p.clamp_min, p.clamp_max, mu.y, bi.y));
+              const int q2 = round_saturate_i8(transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z));
+              const int q3 = round_saturate_i8(transform_float_x2(x[4 * k + 3], p.clamp_min, p.clamp_max, mu.w, bi.w));
+              pk[k] = (q0 & 0xFF) | ((q1 & 0xFF) << 8) | ((q2 & 0xFF) << 16) | (static_cast<uint32_t>(q3 & 0xFF) << 24);
+            }
+            int8_t* o = static_cast<int8_t*>(p.out) + static_cast<size_t>(m) * p.cout + c0;
+            if ((p.cout & 15) == 0 && c0 + 32 <= p.cout) {
+              reinterpret_cast<uint4*>(o)[0] = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+              reinterpret_cast<uint4*>(o)[1] = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+            } else {
+#pragma unroll
+              for (int k = 0; k < 32; ++k)
+                if (c0 + k < p.cout) o[k] = static_cast<int8_t>((pk[k >> 2] >> (8 * (k & 3))) & 0xFF);
+            }
+          }
+        } else {  // LCE_OUT_BITPACKED: bit = acc > threshold (output_transform.h:164-167)
+          uint32_t bits = 0;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) {
+            const int4 th = __ldg(reinterpret_cast<const int4*>(p.thr + c0) + k);
+            bits |= (((x[4 * k] >> 1) > th.x ? 1u : 0u) | ((x[4 * k + 1] >> 1) > th.y ? 2u : 0u) |
+                     ((x[4 * k + 2] >> 1) > th.z ? 4u : 0u) | ((x[4 * k + 3] >> 1) > th.w ? 8u : 0u)) << (4 * k);
+          }
+          const int valid = p.cout - c0;
+          if (valid < 32) bits &= (1u << valid) - 1u;
+          if (row_ok) static_cast<int32_t*>(p.out)[static_cast<size_t>(m) * p.cw_out + (c0 >> 5)] = static_cast<int32_t>(bits);
+        }
+      }
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+
+  __syncwarp();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace lce
+#endif

@@ -129,6 +129,14 @@ void lce_b200_bgemm_destroy(lce_b200_bgemm* plan);
 /* Number of kernels this library has launched in this process (bench.py's
  * `gpu_launches`). */
 uint64_t lce_b200_launch_count(void);
+/* Diagnostics. path_counts: inner-product launches so far by kernel family
+ * {tcgen05 (lce_b200_tc.cuh), mma.sync int8 (lce_b200_imma.cuh), XOR + POPC
+ * (lce_b200_kernels.cuh)} -- the tests use it to prove which kernel ran.
+ * tc_debug: the tcgen05 kernel's deadlock-watchdog record; out[7] != 0 means a
+ * wait timed out ({barrier tag, block, thread, parity, count} in out[0..4]);
+ * reading clears the flag. */
+void lce_b200_path_counts(uint64_t out[3]);
+int lce_b200_tc_debug(int32_t out[8]);
 
 #ifdef __cplusplus
 }
