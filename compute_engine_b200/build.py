@@ -47,6 +47,8 @@ def build_cuda(force=False, verbose=False):
         return out
     cus = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
     cmd = [_nvcc(), *NVCC_FLAGS, "-I", INC, *cus, "-o", out]
+    if os.environ.get("LCE_TC_PROF_BUILD") == "1":      # development: per-role cycle counters
+        cmd.insert(1, "-DLCE_TC_PROF=1")
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.run(cmd, check=True)

@@ -55,6 +55,7 @@ EXPORTS = [
     "lce_b200_quantize", "lce_b200_dequantize", "lce_b200_bmaxpool_out_shape",
     "lce_b200_bmaxpool", "lce_b200_bconv2d_out_shape", "lce_b200_bconv2d_create",
     "lce_b200_bconv2d_set_input_shape", "lce_b200_bconv2d_get_desc",
+    "lce_b200_bconv2d_set_zero_padding_mode", "lce_b200_path_counts", "lce_b200_tc_debug",
     "lce_b200_bconv2d_run", "lce_b200_bconv2d_run_fused", "lce_b200_bconv2d_run_f32", "lce_b200_bconv2d_run_host",
     "lce_b200_bconv2d_destroy", "lce_b200_bgemm_create", "lce_b200_bgemm_run",
     "lce_b200_bgemm_destroy", "lce_b200_launch_count",
@@ -187,6 +188,11 @@ class BConv2d:
     def set_input_shape(self, batch, in_h, in_w):
         _check(lib().lce_b200_bconv2d_set_input_shape(self._h, batch, in_h, in_w))
         self.desc.batch, self.desc.in_h, self.desc.in_w = batch, in_h, in_w
+
+    def set_zero_padding_mode(self, mode):
+        """0: the reference kernel's integers (reference.h:100-103); 1: the optimised kernels'
+        float correction (zero_padding_correction.h) -- see include/lce_b200_types.h."""
+        _check(lib().lce_b200_bconv2d_set_zero_padding_mode(self._h, int(mode)))
 
     def out_shape(self):
         d = BconvDesc()

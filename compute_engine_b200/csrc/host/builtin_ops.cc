@@ -335,6 +335,23 @@ TfLiteStatus ReluInvoke(TfLiteContext* c, TfLiteNode* n) {
   return kTfLiteOk;
 }
 
+// --------------------------------- DEQUANTIZE -------------------------------- //
+// int8 / uint8 -> float32 with the input tensor's (scale, zero_point): TF/lite/kernels/dequantize.cc.
+TfLiteStatus DequantPrepare(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  TfLiteTensor* o = T(c, n->outputs, 0);
+  B_ENSURE(c, a && o && (a->type == kTfLiteInt8 || a->type == kTfLiteUInt8) && o->type == kTfLiteFloat32,
+           "DEQUANTIZE: only int8 / uint8 -> float32 is supported");
+  return SameShapePrepare(c, n);
+}
+TfLiteStatus DequantInvoke(TfLiteContext* c, TfLiteNode* n) {
+  const TfLiteTensor* a = T(c, n->inputs, 0);
+  B_CAPI(c, lce_b200_dequantize_affine(a->type == kTfLiteInt8 ? LCE_T_INT8 : LCE_T_BOOL, a->data.raw,
+                                       T(c, n->outputs, 0)->data.f, Count(a), a->params.scale,
+                                       a->params.zero_point, lce_b200_get_stream()));
+  return kTfLiteOk;
+}
+
 // ----------------------------------- MEAN ----------------------------------- //
 TfLiteStatus MeanPrepare(TfLiteContext* c, TfLiteNode* n) {
   const TfLiteTensor* in = T(c, n->inputs, 0);
@@ -538,6 +555,8 @@ void RegisterBuiltinOps(OpResolver* r) {
   r->AddBuiltin(34, &pad);   // PAD
   r->AddBuiltin(60, &pad);   // PADV2
   r->AddBuiltin(2, &concat);  // CONCATENATION
+  static TfLiteRegistration dequant = {Init, Free, DequantPrepare, DequantInvoke};
+  r->AddBuiltin(6, &dequant);  // DEQUANTIZE
 }
 
 }  // namespace lce_b200

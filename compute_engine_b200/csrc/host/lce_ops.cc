@@ -155,7 +155,11 @@ struct BconvOpData {
   bool successfully_initialized = false;
   bool plan_stale = true;
   lce_b200_bconv2d* plan = nullptr;
-  const void* plan_filter = nullptr;  // constants the plan was built from
+  // what the plan was built from (constant inputs, output type / quantisation, activation)
+  const void* plan_key[4] = {nullptr, nullptr, nullptr, nullptr};
+  int plan_out_type = -1, plan_zero_point = 0, plan_activation = -1;
+  float plan_scale = 0.0f;
+  int zp_mode = LCE_ZERO_PADDING_REFERENCE;  // set by Prepare from the registration
   Staging staging;
   ~BconvOpData() { lce_b200_bconv2d_destroy(plan); }
 };
@@ -245,14 +249,26 @@ TfLiteStatus BconvPrepare(TfLiteContext* context, TfLiteNode* node) {
   d.out_type = output->type == kTfLiteFloat32 ? LCE_OUT_FLOAT
                : output->type == kTfLiteInt8  ? LCE_OUT_INT8
                                               : LCE_OUT_BITPACKED;
-  // zero padding legality: bconv2d.cc:188-200. The CUDA kernel implements the
-  // reference kernel's integer semantics, so its own registration uses that rule.
+  // Zero padding: legality as bconv2d.cc:188-200 and, with it, WHICH of the reference's two
+  // results this node reproduces (LCE_ZERO_PADDING_*, include/lce_b200_types.h): the reference
+  // registration computes the reference kernel's integers; the optimised registrations -- the
+  // reference's default Register_BCONV_2D among them -- one-padding plus the float correction of
+  // zero_padding_correction.h. The default registration accepts the union of both rules and
+  // follows the optimised kernels wherever they are legal.
+  op->zp_mode = LCE_ZERO_PADDING_REFERENCE;
   if (d.padding == LCE_PADDING_SAME && d.pad_value == 0) {
     const bool ref_rule = d.channels_in % 2 == 0;
     const bool opt_rule = output->type == kTfLiteFloat32 && d.activation == LCE_ACT_NONE;
-    const bool legal = (kernel_type == KernelType::kReference || kernel_type == KernelType::kCuda)
-                           ? ref_rule
-                           : opt_rule;
+    bool legal;
+    if (kernel_type == KernelType::kReference) {
+      legal = ref_rule;
+    } else if (kernel_type == KernelType::kCuda) {
+      legal = ref_rule || opt_rule;
+      if (opt_rule) op->zp_mode = LCE_ZERO_PADDING_CORRECTION;
+    } else {
+      legal = opt_rule;
+      op->zp_mode = LCE_ZERO_PADDING_CORRECTION;
+    }
     LCE_ENSURE_MSG(context, legal,
                    "Zero-padding is only supported by the reference kernel with an even "
                    "number of input channels, or when using "
@@ -374,7 +390,18 @@ TfLiteStatus BconvEnsurePlan(TfLiteContext* context, TfLiteNode* node) {
   if (ot != kTfLiteFloat32 && ot != kTfLiteInt8 && ot != kTfLiteInt32) return kTfLiteError;
 
   if (op->plan_stale) {
-    if (op->plan && op->plan_filter == filter->data.raw_const) {
+    // The re-tiled weights and folded epilogue vectors are reused only while every constant
+    // input, the output type and its quantisation are what the plan was built from; the reference
+    // redoes its OneTimeSetup on every Prepare (bconv2d.cc:295-297).
+    const void* key[4] = {filter->data.raw_const, post_mul ? post_mul->data.raw_const : nullptr,
+                          post_bias ? post_bias->data.raw_const : nullptr,
+                          thresholds ? thresholds->data.raw_const : nullptr};
+    const bool same = op->plan && op->plan_key[0] == key[0] && op->plan_key[1] == key[1] &&
+                      op->plan_key[2] == key[2] && op->plan_key[3] == key[3] &&
+                      op->plan_out_type == op->desc.out_type && op->plan_scale == op->desc.out_scale &&
+                      op->plan_zero_point == op->desc.out_zero_point &&
+                      op->plan_activation == op->desc.activation;
+    if (same) {
       LCE_ENSURE_CAPI(context, lce_b200_bconv2d_set_input_shape(op->plan, op->desc.batch,
                                                                  op->desc.in_h, op->desc.in_w));
     } else {
@@ -385,8 +412,13 @@ TfLiteStatus BconvEnsurePlan(TfLiteContext* context, TfLiteNode* node) {
                           &op->desc, filter->data.i32, post_mul ? post_mul->data.f : nullptr,
                           post_bias ? post_bias->data.f : nullptr,
                           thresholds ? thresholds->data.i32 : nullptr, &op->plan));
-      op->plan_filter = filter->data.raw_const;
+      for (int i = 0; i < 4; ++i) op->plan_key[i] = key[i];
+      op->plan_out_type = op->desc.out_type;
+      op->plan_scale = op->desc.out_scale;
+      op->plan_zero_point = op->desc.out_zero_point;
+      op->plan_activation = op->desc.activation;
     }
+    LCE_ENSURE_CAPI(context, lce_b200_bconv2d_set_zero_padding_mode(op->plan, op->zp_mode));
     op->plan_stale = false;
   }
   (void)input;

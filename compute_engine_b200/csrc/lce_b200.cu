@@ -303,14 +303,14 @@ int build_tc_weights(GemmCore* c, const int32_t* d_filter, bool want_tap_popc) {
   }
   c->tc_n_chunks = cdiv(Cw, c->tc_CcB);
   const int cc_last = Cw - (c->tc_n_chunks - 1) * c->tc_CcB;
-  c->tc_S_full = cdiv(c->taps * c->tc_CcB, 4);
-  c->tc_S_last = cdiv(c->taps * cc_last, 4);
+  c->tc_S_full = cdiv(c->taps * c->tc_CcB, lce::tc::kWS);
+  c->tc_S_last = cdiv(c->taps * cc_last, lce::tc::kWS);
   c->tc_S_t = (c->tc_n_chunks - 1) * c->tc_S_full + c->tc_S_last;
   c->tc_ldc = c->tc_n_tiles * c->tc_BN;
-  const long long units = static_cast<long long>(c->tc_n_tiles) * c->tc_S_t * c->tc_BN * 4;
+  const long long units = static_cast<long long>(c->tc_n_tiles) * c->taps * Cw * c->tc_BN;
   CUDA_OK(cudaMalloc(&c->tc_wt, static_cast<size_t>(units) * 32));
   lce::tc::expand_weights_tc_kernel<<<grid_for(units, 256, 1 << 22), 256>>>(
-      d_filter, c->tc_wt, c->cout, c->taps, Cw, c->tc_CcB, c->tc_n_chunks, c->tc_BN, c->tc_S_full, c->tc_S_t, units);
+      d_filter, c->tc_wt, c->cout, c->taps, Cw, c->tc_CcB, c->tc_BN, units);
   if (launch_check("expand_weights_tc_kernel")) return 1;
   CUDA_OK(cudaMalloc(&c->tc_wpop2, static_cast<size_t>(c->tc_ldc) * 4));
   CUDA_OK(cudaMemset(c->tc_wpop2, 0, static_cast<size_t>(c->tc_ldc) * 4));
@@ -410,35 +410,40 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   else raw_stage = static_cast<size_t>(cdiv(c.tc_max_px, 128)) * 128 * c.tc_CcB * 4;
   raw_stage = (raw_stage + 1023) & ~size_t{1023};
   t.raw_stage_bytes = static_cast<int>(raw_stage);
-  const size_t stage_bytes = static_cast<size_t>(c.tc_BN) * 128;
+  const size_t stage_bytes = static_cast<size_t>(c.tc_BN) * 32 * T::kWS;     // one ring slot
+  const size_t resident_bytes = static_cast<size_t>(c.tc_BN) * 32 * t.taps * c.Cw_pg;  // all K words, dense
   const bool has_res = p.residual != nullptr;
   int nS = tma_out ? (has_res ? T::kMaxNS : 2) : 0;
-  const size_t fixed = T::kNR * raw_stage + T::kBarBytes;
-  if (fixed + 2 * T::kSlotBytes + 4 * stage_bytes > kTcSmemBudget) return -1;
-  auto stages_that_fit = [&](int ns) {
-    return static_cast<int>((kTcSmemBudget - fixed - static_cast<size_t>(ns) * T::kSlotBytes) / stage_bytes);
-  };
+  const size_t fixed = T::kNR * raw_stage + T::kBarBytes + T::kTabBytes;
+  if (fixed + 2 * T::kSlotBytes + 3 * stage_bytes > kTcSmemBudget) return -1;
+  auto room = [&](int ns) { return kTcSmemBudget - fixed - static_cast<size_t>(ns) * T::kSlotBytes; };
   const bool can_reside = c.tc_n_tiles == 1 && c.tc_S_t <= T::kMaxNB;
-  if (can_reside && stages_that_fit(nS) < c.tc_S_t && has_res && stages_that_fit(2) >= c.tc_S_t) nS = 2;
-  int nB = std::min(stages_that_fit(nS), T::kMaxNB);
-  if (can_reside && nB >= c.tc_S_t) {
+  if (can_reside && room(nS) < resident_bytes && has_res && room(2) >= resident_bytes) nS = 2;
+  size_t b_bytes;
+  if (can_reside && room(nS) >= resident_bytes) {
     t.b_resident = 1;
-    nB = c.tc_S_t;
+    t.nB = c.tc_S_t;
+    b_bytes = (resident_bytes + 1023) & ~size_t{1023};
   } else {
     t.b_resident = 0;
-    if (nB < 4) return -1;
-    nB = std::min(nB, 12);  // a deeper ring buys nothing; leave the rest to L1
+    const int nB = std::min<int>(static_cast<int>(room(nS) / stage_bytes), 6);
+    if (nB < 3) return -1;
+    t.nB = nB;
+    b_bytes = nB * stage_bytes;
   }
-  t.nB = nB; t.nS = nS;
-  t.off_raw = static_cast<int>(nB * stage_bytes);
+  t.nS = nS;
+  t.Kw_total = t.taps * c.Cw_pg;
+  t.off_raw = static_cast<int>(b_bytes);
   t.off_slots = t.off_raw + T::kNR * t.raw_stage_bytes;
-  t.off_bar = t.off_slots + nS * T::kSlotBytes;
+  t.off_tab = t.off_slots + nS * T::kSlotBytes;
+  t.off_bar = t.off_tab + T::kTabBytes;
   const size_t smem = static_cast<size_t>(t.off_bar) + T::kBarBytes;
   t.clamp_min = p.clamp_min; t.clamp_max = p.clamp_max;
   t.has_res = has_res ? 1 : 0; t.residual_act = p.residual_act;
   t.cw_out = p.cw_out; t.zp_half = p.zp_half; t.ldc = c.tc_ldc;
   t.wt = c.tc_wt; t.mul = p.mul; t.bias = p.bias; t.wpop2 = c.tc_wpop2; t.thr = p.thr;
   t.tap_popc_t = p.tap_popc != nullptr ? c.tc_tap_popc_t : nullptr;
+  t.zp_float = p.zp_float; t.cin_pg = p.cin_pg;
   t.out = p.out; t.packed_out = p.packed_out;
   t.fd_ohw = lce::make_fastdiv(static_cast<uint32_t>(ohw));
   t.fd_ow = lce::make_fastdiv(p.OW);
@@ -487,6 +492,30 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   }
   const long long items = static_cast<long long>(t.n_tiles) * t.m_tiles;
   const int grid = static_cast<int>(std::min<long long>(items, num_sms()));
+  static long long* d_prof = nullptr;
+  static const bool prof_on = [] { const char* e = getenv("LCE_B200_TC_PROF"); return e && e[0] == '1'; }();
+  if (prof_on) {
+    // development aid: per-role cycle counters of block 0, printed after a synchronising copy
+    if (!d_prof) cudaMalloc(&d_prof, 16 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 16 * 8 * sizeof(long long), s);
+    t.prof = d_prof;
+  }
+  struct ProfDump {
+    long long* d; cudaStream_t s; const T::TcParams* t; int grid;
+    ~ProfDump() {
+      if (!d) return;
+      long long h[128];
+      cudaStreamSynchronize(s);
+      cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[tc prof] M=%lld BN=%d S_t=%d nB=%d res=%d resident=%d items=%d grid=%d\n", t->M, t->BN, t->S_t,
+              t->nB, t->has_res, t->b_resident, t->n_tiles * t->m_tiles, grid);
+      const char* names[16] = {"act-prod", "mma", "w-prod", "res-prod", "exp0", "exp1", "exp2", "exp3", "exp4", "exp5", "exp6",
+                               "exp7", "epi0", "epi1", "epi2", "epi3"};
+      for (int w : {0, 1, 2, 3, 4, 8, 12})
+        fprintf(stderr, "[tc prof]  %-8s total=%lld  c1=%lld c2=%lld c3=%lld c4=%lld c5=%lld c6=%lld\n", names[w], h[w * 8],
+                h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6]);
+    }
+  } prof_dump{prof_on ? d_prof : nullptr, s, &t, grid};
   switch (c.tc_V) {
     case 4: return launch_tc_v<4>(c.out_type, tm_in, tm_res, tm_out, t, grid, smem, s);
     case 2: return launch_tc_v<2>(c.out_type, tm_in, tm_res, tm_out, t, grid, smem, s);
@@ -571,6 +600,7 @@ bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) ==
 // ------------------------------------------------------------------------- //
 struct lce_b200_bconv2d {
   lce_bconv2d_desc d;
+  int zp_mode = LCE_ZERO_PADDING_REFERENCE;
   int out_h = 0, out_w = 0, pad_h = 0, pad_w = 0;
   GemmCore core;
   int32_t* packed_scratch = nullptr;  // run_f32: packed activations
@@ -744,7 +774,11 @@ int lce_b200_bconv2d_create(const lce_bconv2d_desc* d, const int32_t* filter,
       d->out_type != LCE_OUT_BITPACKED)
     return fail("Supported output types are int8, int32, and float32.");  // bconv2d.cc:158-162
   const bool zero_pad = d->padding == LCE_PADDING_SAME && d->pad_value == 0;
-  if (zero_pad && d->channels_in % 2 != 0)  // bconv2d.cc:188-200, reference-kernel rule
+  // bconv2d.cc:188-200: the reference kernel's rule (even channels_in) or the optimised kernels'
+  // (float output, no fused activation); the plan starts in the mode whose rule holds
+  const bool zp_ref_rule = d->channels_in % 2 == 0;
+  const bool zp_opt_rule = d->out_type == LCE_OUT_FLOAT && d->activation == LCE_ACT_NONE;
+  if (zero_pad && !zp_ref_rule && !zp_opt_rule)
     return fail("Zero-padding is only supported by the reference kernel with an even number of "
                 "input channels, or when using float output with no fused activation function.");
   if (d->out_type == LCE_OUT_BITPACKED) {
@@ -756,6 +790,7 @@ int lce_b200_bconv2d_create(const lce_bconv2d_desc* d, const int32_t* filter,
 
   auto* plan = new lce_b200_bconv2d();
   plan->d = *d;
+  plan->zp_mode = (zero_pad && !zp_ref_rule) ? LCE_ZERO_PADDING_CORRECTION : LCE_ZERO_PADDING_REFERENCE;
   plan->out_h = oh; plan->out_w = ow; plan->pad_h = ph; plan->pad_w = pw;
   GemmCore& c = plan->core;
   c.groups = d->groups;
@@ -821,6 +856,24 @@ int lce_b200_bconv2d_set_input_shape(lce_b200_bconv2d* plan, int batch, int in_h
   return 0;
 }
 
+int lce_b200_bconv2d_set_zero_padding_mode(lce_b200_bconv2d* plan, int mode) {
+  const lce_bconv2d_desc& d = plan->d;
+  if (mode == LCE_ZERO_PADDING_CORRECTION) {
+    if (d.padding == LCE_PADDING_SAME && d.pad_value == 0 &&
+        !(d.out_type == LCE_OUT_FLOAT && d.activation == LCE_ACT_NONE))
+      return fail("Zero-padding is only supported by the reference kernel with an even number of "
+                  "input channels, or when using float output with no fused activation function.");
+  } else if (mode == LCE_ZERO_PADDING_REFERENCE) {
+    if (d.padding == LCE_PADDING_SAME && d.pad_value == 0 && d.channels_in % 2 != 0)
+      return fail("Zero-padding is only supported by the reference kernel with an even number of "
+                  "input channels, or when using float output with no fused activation function.");
+  } else {
+    return fail("bconv2d: unknown zero-padding mode %d", mode);
+  }
+  plan->zp_mode = mode;
+  return 0;
+}
+
 int lce_b200_bconv2d_get_desc(const lce_b200_bconv2d* plan, lce_bconv2d_desc* d, int* out_h,
                               int* out_w) {
   *d = plan->d;
@@ -882,7 +935,31 @@ static int bconv_run_impl(lce_b200_bconv2d* plan, const int32_t* in_dev, void* o
     return fail("bconv2d: input pointer must be %d-byte aligned", 4 * c.V);
   if (d.out_type == LCE_OUT_BITPACKED && !p.bp_fast)
     CUDA_OK(cudaMemsetAsync(out_dev, 0, bconv_out_bytes(plan), s));
-  return launch_conv(c, p, s);
+  const bool zp_float = c.tap_popc != nullptr && plan->zp_mode == LCE_ZERO_PADDING_CORRECTION;
+  if (!zp_float) return launch_conv(c, p, s);
+  // the optimised kernels' zero padding: one-padding accumulators + a float correction. The
+  // tcgen05 kernel does it in its epilogue; the others run unfused and a tail pass finishes.
+  p.zp_float = 1;
+  p.cin_pg = d.channels_in / d.groups;
+  if (c.tc_ok) {
+    const int rc = tc_launch(c, p, s);
+    if (rc >= 0) return rc;
+  }
+  lce::ConvKParams q = p;
+  q.tap_popc = nullptr; q.residual = nullptr; q.packed_out = nullptr; q.res_stage = 0; q.zp_float = 0;
+  const bool tc_was = c.tc_ok;
+  c.tc_ok = false;
+  const int rc = launch_conv(c, q, s);
+  c.tc_ok = tc_was;
+  if (rc) return rc;
+  lce::ZpcTailParams z;
+  z.out = static_cast<float*>(out_dev); z.mul = c.mul; z.tap_popc = c.tap_popc;
+  z.residual = residual; z.packed_out = packed_out; z.M = p.M;
+  z.H = p.H; z.W = p.W; z.OH = p.OH; z.OW = p.OW; z.KH = p.KH; z.KW = p.KW;
+  z.sh = p.sh; z.sw = p.sw; z.dh = p.dh; z.dw = p.dw;
+  z.cout = c.cout; z.cin_pg = p.cin_pg; z.cw_out = p.cw_out; z.residual_act = residual_act;
+  lce::zpc_tail_kernel<<<grid_for(p.M * cdiv(c.cout, 32) * 32, 256), 256, 0, s>>>(z);
+  return launch_check("zpc_tail_kernel");
 }
 
 int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev, void* out_dev,

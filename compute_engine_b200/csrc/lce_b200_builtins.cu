@@ -1205,6 +1205,33 @@ int make_geom(const lce_f32_conv_desc* d, ConvGeom* g) {
 
 }  // namespace
 
+// DEQUANTIZE (TF/lite/kernels/internal/reference/dequantize.h:32-49): out = float(scale * (q - zp)),
+// the product in double as there. 16 quantised values (one 128-bit load) per thread.
+template <typename Q>
+__global__ void __launch_bounds__(256) dequantize_affine_kernel(const Q* __restrict__ in, float* __restrict__ out,
+                                                                long long n, double scale, int zp) {
+  const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+  const long long n16 = n / 16;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n16; i += stride) {
+    const uint4 v = __ldcs(reinterpret_cast<const uint4*>(in) + i);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+    float4* o = reinterpret_cast<float4*>(out) + i * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float r[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const Q q = static_cast<Q>((w[j] >> (8 * k)) & 0xFFu);
+        r[k] = static_cast<float>(scale * static_cast<double>(static_cast<int>(q) - zp));
+      }
+      o[j] = make_float4(r[0], r[1], r[2], r[3]);
+    }
+  }
+  for (long long i = n16 * 16 + blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n; i += stride)
+    out[i] = static_cast<float>(scale * static_cast<double>(static_cast<int>(in[i]) - zp));
+}
+
+
 extern "C" {
 
 int lce_b200_f32_conv_out_shape(const lce_f32_conv_desc* d, int* out_h, int* out_w) {
@@ -1521,6 +1548,24 @@ int lce_b200_f32_softmax(const float* in, float* out, int64_t rows, int cols, fl
   softmax_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
       in, out, rows, cols, beta);
   return launch_check("softmax_kernel");
+}
+
+int lce_b200_dequantize_affine(int in_type, const void* in, float* out, int64_t n, double scale,
+                               int32_t zero_point, void* stream) {
+  if (n <= 0) return 0;
+  if ((reinterpret_cast<uintptr_t>(in) & 15u) != 0 || (reinterpret_cast<uintptr_t>(out) & 15u) != 0)
+    return fail("dequantize: buffers must be 16-byte aligned");
+  const unsigned grid = static_cast<unsigned>(std::min<long long>((n / 16 + 256) / 256, 148 * 16));
+  if (in_type == LCE_T_INT8) {
+    dequantize_affine_kernel<int8_t><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const int8_t*>(in), out, n, scale,
+                                                                          zero_point);
+  } else if (in_type == LCE_T_BOOL) {   // the uint8 code of the LCE_T_* enum
+    dequantize_affine_kernel<uint8_t><<<grid, 256, 0, as_stream(stream)>>>(static_cast<const uint8_t*>(in), out, n, scale,
+                                                                           zero_point);
+  } else {
+    return fail("dequantize: unsupported quantised type %d", in_type);
+  }
+  return launch_check("dequantize_affine_kernel");
 }
 
 int lce_b200_pad4d_32(const void* in, void* out, const int32_t* in_dims,

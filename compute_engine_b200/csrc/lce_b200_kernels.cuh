@@ -89,6 +89,7 @@ struct ConvKParams {
   int bp_fast;       // bitpacked output: tiles start on a 32-channel boundary
   int res_stage;     // residual rows are staged through shared memory (kResStageBytes extra)
   const int32_t* wpop;  // IMMA path: popcount of each channel's whole filter row
+  int zp_float, cin_pg; // zero padding with the optimised kernels' float correction (host-side switch)
   FastDiv fd_ohw, fd_ow, fd_cwv, fd_kw, fd_tpg;  // / (OH*OW), / OW, / CwV, / KW, / tiles_per_group
   long long img_words;  // H * W * Cw_total (< 2^31, checked by the host)
 };
@@ -767,6 +768,80 @@ __global__ void tap_popc_kernel(const int32_t* __restrict__ filter, int32_t* __r
   int s = 0;
   for (int w = 0; w < Cw_pg; ++w) s += __popc(static_cast<uint32_t>(f[w]));
   out[idx] = s;
+}
+
+// ------------------------------------------------------------------------- //
+// Zero padding with the optimised reference kernels' float correction, for the plans that do not
+// run on the tcgen05 kernel (which has it in its epilogue): the convolution ran with one-padding
+// and no fused tail; this pass adds the correction to the edge pixels
+// (zero_padding_correction.h:178-299, the case analysis restated literally), then the fused ADD /
+// activation / sign-pack tail if there is one. One warp per (pixel, 32 channels).
+// ------------------------------------------------------------------------- //
+struct ZpcTailParams {
+  float* out;
+  const float* mul;          // folded multiplier = -post_activation_multiplier
+  const int32_t* tap_popc;   // [cout][taps]
+  const float* residual;
+  int32_t* packed_out;
+  long long M;
+  int H, W, OH, OW, KH, KW, sh, sw, dh, dw;
+  int cout, cin_pg, cw_out, residual_act;
+};
+__global__ void __launch_bounds__(256) zpc_tail_kernel(const ZpcTailParams p) {
+  const int lane = threadIdx.x & 31;
+  const int cw = (p.cout + 31) >> 5;
+  const long long n_warps = p.M * cw;
+  const long long stride = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  const int eff_w = (p.KW - 1) * p.dw + 1, eff_h = (p.KH - 1) * p.dh + 1;
+  const int left_off = ((p.OW - 1) * p.sw + eff_w - p.W) / 2;
+  const int top_off = ((p.OH - 1) * p.sh + eff_h - p.H) / 2;
+  const int taps = p.KH * p.KW;
+  for (long long w = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5; w < n_warps; w += stride) {
+    const long long m = w / cw;
+    const int c = static_cast<int>(w - m * cw) * 32 + lane;
+    const long long r = m % (static_cast<long long>(p.OH) * p.OW);
+    const int oy = static_cast<int>(r / p.OW), ox = static_cast<int>(r % p.OW);
+    const int o_top = top_off - oy * p.sh, o_bot = -o_top - p.H + eff_h;
+    const int o_left = left_off - ox * p.sw, o_right = -o_left - p.W + eff_w;
+    int cs = -1, X = 0, Y = 0;
+    if (!(o_left <= 0 && o_right <= 0 && o_top <= 0 && o_bot <= 0)) {
+      if (o_right <= 0 && o_top > 0 && o_bot < 0) { cs = 0; X = max(o_left, 0); Y = o_top; }
+      else if (o_left < 0 && o_right > 0 && o_bot <= 0) { cs = 1; X = o_right; Y = max(o_top, 0); }
+      else if (o_left > 0 && o_right < 0 && o_top <= 0) { cs = 2; X = o_left; Y = max(o_bot, 0); }
+      else if (o_left <= 0 && o_top < 0 && o_bot > 0) { cs = 3; X = max(o_right, 0); Y = o_bot; }
+    }
+    if (cs < 0 && p.residual == nullptr && p.packed_out == nullptr) continue;   // interior, nothing fused
+    float y = 0.0f;
+    const bool ok = c < p.cout;
+    if (ok) {
+      y = p.out[m * p.cout + c];
+      if (cs >= 0) {
+        int corr = 0;
+        for (int fy = 0; fy < p.KH; ++fy)
+          for (int fx = 0; fx < p.KW; ++fx) {
+            const int efx = p.dw * fx, efy = p.dh * fy;
+            bool counted;
+            if (cs == 0) counted = efy < Y || efx < X;
+            else if (cs == 1) counted = efy < Y || (eff_w - efx) <= X;
+            else if (cs == 2) counted = (eff_h - efy) <= Y || efx < X;
+            else counted = (eff_h - efy) <= Y || (eff_w - efx) <= X;
+            if (counted) corr += p.cin_pg - 2 * p.tap_popc[static_cast<size_t>(c) * taps + fy * p.KW + fx];
+          }
+        y = __fadd_rn(y, __fmul_rn(p.mul[c], static_cast<float>(corr)));
+      }
+      if (p.residual != nullptr) {
+        y = __fadd_rn(y, p.residual[m * p.cout + c]);
+        if (p.residual_act == LCE_ACT_RELU) y = fmaxf(y, 0.0f);
+        else if (p.residual_act == LCE_ACT_RELU6) y = fminf(fmaxf(y, 0.0f), 6.0f);
+        else if (p.residual_act == LCE_ACT_RELU_N1_TO_1) y = fminf(fmaxf(y, -1.0f), 1.0f);
+      }
+      p.out[m * p.cout + c] = y;
+    }
+    if (p.packed_out != nullptr) {
+      const uint32_t word = __ballot_sync(0xffffffffu, ok && y < 0.0f);
+      if (lane == 0) p.packed_out[m * p.cw_out + (c >> 5)] = static_cast<int32_t>(word);
+    }
+  }
 }
 
 // ------------------------------------------------------------------------- //

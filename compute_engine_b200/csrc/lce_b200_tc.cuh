@@ -9,12 +9,14 @@
 // words (types.h:41-47); bytes exist only in TMEM (activations) and in a plan-time expansion of
 // the static weights.
 //
-// One persistent CTA per SM, 16 warps, warp-specialised:
+// One persistent CTA per SM, 20 warps, warp-specialised:
 //   w0        activation producer  TMA (cp.async.bulk.tensor, SASS UTMALDG) of the packed HALO
 //                                  of a 128-pixel tile: the contiguous pixel range its taps touch,
 //                                  once per tile -- no im2col replication anywhere
-//   w1        MMA issuer           one lane issues tcgen05.mma.cta_group::1.kind::i8, A from TMEM,
-//                                  B from shared memory, D (128 x BN int32) in TMEM, two D buffers
+//   w1        MMA issuer           the warp runs converged so every descriptor lives in uniform
+//                                  registers; one elected lane issues tcgen05.mma.cta_group::1
+//                                  .kind::i8, A from TMEM, B from shared memory, D (128 x BN int32)
+//                                  in TMEM, two D buffers
 //   w2        weight producer      cp.async.bulk of pre-expanded int8 stages (resident in shared
 //                                  memory for the whole kernel when they fit, else a ring)
 //   w3        shortcut producer    TMA tiles of the residual (fused ADD), SWIZZLE_128B
@@ -25,10 +27,11 @@
 //                                  2^(s&3); the weight byte there is +-(8 >> (s&3)), so every
 //                                  product is +-8 and D holds 8 * sum a*w') and writes them with
 //                                  tcgen05.st; two warps per TMEM lane quadrant take alternate stages
-//   w12..w15  epilogue             tcgen05.ld -> OutputTransform (output_transform.h:94-168,
+//   w12..w19  epilogue             tcgen05.ld -> OutputTransform (output_transform.h:94-168,
 //                                  unfused fmul + fadd) [+ shortcut, activation, next layer's sign
-//                                  bits] -> swizzled shared memory -> TMA store (UTMASTG)
-// Stage = 4 K-words = 128 bits of K = four K=32 MMAs; 8 A stages live in TMEM columns 256..511.
+//                                  bits] -> swizzled shared memory -> TMA store (UTMASTG); two warps
+//                                  per TMEM lane quadrant take alternate 32-channel chunks
+// Stage = 8 K-words = 256 bits of K = eight K=32 MMAs; 4 A stages live in TMEM columns 256..511.
 #ifndef LCE_B200_TC_CUH_
 #define LCE_B200_TC_CUH_
 
@@ -39,14 +42,19 @@
 namespace lce {
 namespace tc {
 
+#ifndef LCE_TC_PROF
+#define LCE_TC_PROF 0   // 1: per-role cycle counters (build with -DLCE_TC_PROF=1, run with LCE_B200_TC_PROF=1)
+#endif
 constexpr int kBM = 128;
-constexpr int kThreads = 512;
-constexpr int kNA = 8;            // A stages in TMEM, 32 columns each
+constexpr int kThreads = 640;
+constexpr int kWS = 8;            // K words per stage
+constexpr int kNA = 4;            // A stages in TMEM, 64 columns each
 constexpr int kNR = 2;            // activation-halo stages
 constexpr int kMaxNB = 32;        // weight stages in shared memory (barrier array size)
 constexpr int kMaxNS = 4;         // epilogue staging slots
 constexpr int kSlotBytes = kBM * 128;  // 128 rows x 32 columns x 4 B
-constexpr int kFirstExpWarp = 4, kNumExpWarps = 8, kFirstEpiWarp = 12;
+constexpr int kFirstExpWarp = 4, kNumExpWarps = 8, kFirstEpiWarp = 12, kNumEpiWarps = 8;
+constexpr int kTabBytes = 4 * 128 * 4 * 2;   // {mul, bias, wpop2, thr} x 128 channels, double-buffered
 constexpr int kBarBytes = 1024;
 
 struct TcParams {
@@ -62,10 +70,12 @@ struct TcParams {
   int S_full, S_last, S_t;   // weight stages per full / last chunk, per tile
   int nB, b_resident, nS;
   int raw_stage_bytes;
-  int off_raw, off_slots, off_bar;   // byte offsets in dynamic shared memory (weights at 0)
+  int off_raw, off_slots, off_tab, off_bar;   // byte offsets in dynamic shared memory (weights at 0)
+  int Kw_total;          // taps * Cw: K words per output channel
   int clamp_min, clamp_max;
   int has_res, residual_act, cw_out, zp_half, ldc;   // ldc: padded channel count of the tables
-  const uint8_t* wt;       // [n_tiles][S_t][BN x 128 B core-matrix image]
+  int zp_float, cin_pg;  // zero padding as the optimised reference kernels do it (float correction)
+  const uint8_t* wt;       // [n_tiles][stage][BN x (32 * words) B core-matrix image], stages dense
   const float* mul;        // folded multiplier / bias, padded to n_tiles * BN
   const float* bias;
   const int32_t* wpop2;    // 2 * popcount of each channel's filter row
@@ -73,6 +83,7 @@ struct TcParams {
   const int32_t* tap_popc_t;  // [taps][ldc] or nullptr (zero-padding correction)
   void* out;
   int32_t* packed_out;
+  long long* prof;         // optional [16 warps][8] cycle counters of block 0 (LCE_B200_TC_PROF=1)
   FastDiv fd_ohw, fd_ow, fd_kw, fd_cwv_full, fd_cwv_last, fd_mt;
 };
 
@@ -129,11 +140,22 @@ __device__ __forceinline__ void mma_i8_ts(uint32_t d, uint32_t a_tmem, uint64_t 
   asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
                "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc) : "memory");
 }
-// K-major, no swizzle: 8 x 16 B core matrices, K-adjacent ones 128 B apart (LBO), 8-row groups
-// 1024 B apart (SBO); descriptor version 1 (Blackwell). Verified on hardware by tools/tc_probe.cu.
-__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr) {
-  return static_cast<uint64_t>((saddr & 0x3FFFFu) >> 4) | (static_cast<uint64_t>(128 >> 4) << 16) |
-         (static_cast<uint64_t>(1024 >> 4) << 32) | (1ull << 46);
+// Shared-memory descriptor of the B operand, K-major, no swizzle: 8 x 16 B core matrices, K-adjacent
+// ones 128 B apart (LBO), 8-row groups `sbo` bytes apart; version 1 (Blackwell). Passed as two
+// 32-bit halves so the issuing warp only does 32-bit uniform arithmetic per MMA. Layout verified
+// on hardware by tools/tc_probe.cu.
+__device__ __forceinline__ uint32_t bdesc_lo(uint32_t saddr) { return ((saddr & 0x3FFFFu) >> 4) | ((128u >> 4) << 16); }
+__device__ __forceinline__ uint32_t bdesc_hi(uint32_t sbo) { return (sbo >> 4) | (1u << 14); }
+__device__ __forceinline__ void mma_i8_ts2(uint32_t d, uint32_t a_tmem, uint32_t blo, uint32_t bhi, uint32_t idesc,
+                                           uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\n.reg .b64 bd;\nsetp.ne.b32 p, %5, 0;\nmov.b64 bd, {%2, %3};\n"
+               "tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], bd, %4, p;\n}\n" ::"r"(d), "r"(a_tmem), "r"(blo), "r"(bhi),
+               "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+  return pred != 0;
 }
 // kind::i8 instruction descriptor: D = s32, A = B = s8, both K-major, M = 128
 __host__ __device__ inline uint32_t make_idesc(int N) {
@@ -160,8 +182,8 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32
       "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
       "r"(r[31])
       : "memory");
-  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tma_load_1d(void* dst, const CUtensorMap* tm, uint64_t* bar, int c0) {
   asm volatile("cp.async.bulk.tensor.1d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3}], [%2];" ::"r"(smem_u32(dst)),
                "l"(reinterpret_cast<uint64_t>(tm)), "r"(smem_u32(bar)), "r"(c0) : "memory");
@@ -176,7 +198,22 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, const void* 
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+// profiling aid: wait and add the cycles spent to `acc` when `on`
+__device__ __forceinline__ void mbar_wait_prof(uint64_t* bar, uint32_t parity, int tag, bool on, long long& acc) {
+  if (!on) {
+    mbar_wait_tc(bar, parity, tag);
+    return;
+  }
+  const long long t = clock64();
+  mbar_wait_tc(bar, parity, tag);
+  acc += clock64() - t;
+}
 
 // ------------------------------------------------------------------ index helpers
 struct Pixel { int b, oy, ox; };
@@ -211,6 +248,48 @@ __device__ __forceinline__ long long halo_word_base(const TcParams& p, long long
   return p.mode_flat ? ((px_lo * p.Cw) & ~3LL) : px_lo * p.CcB;
 }
 
+// Zero padding, which taps of output pixel (oy, ox) are corrected.
+//  reference kernel (zp_float == 0): the out-of-bounds taps (reference.h:100-103).
+//  optimised kernels (zp_float == 1): the taps that ApplyCorrection's case analysis counts
+//  (zero_padding_correction.h:39-176,232-285), restated literally -- for every image at least as
+//  large as the dilated filter that is again the set of out-of-bounds taps.
+__device__ __forceinline__ unsigned long long zero_pad_tap_mask(const TcParams& p, int oy, int ox) {
+  unsigned long long mask = 0;
+  if (!p.zp_float) {
+    const int iy0 = oy * p.sh - p.ph, ix0 = ox * p.sw - p.pw;
+    for (int fy = 0; fy < p.KH; ++fy)
+      for (int fx = 0; fx < p.KW; ++fx) {
+        const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
+        if (!(static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)))
+          mask |= 1ull << (fy * p.KW + fx);
+      }
+    return mask;
+  }
+  const int eff_w = (p.KW - 1) * p.dw + 1, eff_h = (p.KH - 1) * p.dh + 1;
+  const int left_off = ((p.OW - 1) * p.sw + eff_w - p.W) / 2;   // zero_padding_correction.h:189-194
+  const int top_off = ((p.OH - 1) * p.sh + eff_h - p.H) / 2;
+  const int o_top = top_off - oy * p.sh, o_bot = -o_top - p.H + eff_h;
+  const int o_left = left_off - ox * p.sw, o_right = -o_left - p.W + eff_w;
+  if (o_left <= 0 && o_right <= 0 && o_top <= 0 && o_bot <= 0) return 0;
+  int cs, X, Y;
+  if (o_right <= 0 && o_top > 0 && o_bot < 0) { cs = 0; X = max(o_left, 0); Y = o_top; }
+  else if (o_left < 0 && o_right > 0 && o_bot <= 0) { cs = 1; X = o_right; Y = max(o_top, 0); }
+  else if (o_left > 0 && o_right < 0 && o_top <= 0) { cs = 2; X = o_left; Y = max(o_bot, 0); }
+  else if (o_left <= 0 && o_top < 0 && o_bot > 0) { cs = 3; X = max(o_right, 0); Y = o_bot; }
+  else return 0;
+  for (int fy = 0; fy < p.KH; ++fy)
+    for (int fx = 0; fx < p.KW; ++fx) {
+      const int efx = p.dw * fx, efy = p.dh * fy;
+      bool counted;
+      if (cs == 0) counted = efy < Y || efx < X;
+      else if (cs == 1) counted = efy < Y || (eff_w - efx) <= X;
+      else if (cs == 2) counted = (eff_h - efy) <= Y || efx < X;
+      else counted = (eff_h - efy) <= Y || (eff_w - efx) <= X;
+      if (counted) mask |= 1ull << (fy * p.KW + fx);
+    }
+  return mask;
+}
+
 // bit 8i+s of w -> byte i of v[s], value 2^(s&3): 9 ALU instructions
 __device__ __forceinline__ void expand_word(uint32_t w, uint32_t* v) {
   v[0] = w & 0x01010101u; v[1] = w & 0x02020202u; v[2] = w & 0x04040404u; v[3] = w & 0x08080808u;
@@ -218,28 +297,30 @@ __device__ __forceinline__ void expand_word(uint32_t w, uint32_t* v) {
   v[4] = h & 0x01010101u; v[5] = h & 0x02020202u; v[6] = h & 0x04040404u; v[7] = h & 0x08080808u;
 }
 
-// Plan time: the weights of one (n tile, stage) as the exact shared-memory image the MMA reads:
-// [BN rows][128 B], no-swizzle K-major core matrices. Stage order = (channel chunk, tap, word).
-// One thread per (n tile, stage, row, word) writes that word's 32 bytes.
+// Plan time: the weights as the exact shared-memory images the MMA reads. K words run in the
+// order (channel chunk, tap, word); each chunk is cut into stages of kWS words; a stage of nw words
+// is [BN / 8 row groups][2 * nw core matrices][8 rows][16 B] (no-swizzle K-major, row-group pitch
+// nw * 256 B) and the stages of one n tile follow one another without padding.
+// One thread per (n tile, K word, row) writes that word's 32 bytes.
 __global__ void expand_weights_tc_kernel(const int32_t* __restrict__ filter, uint8_t* __restrict__ wt, int cout, int taps,
-                                         int Cw, int CcB, int n_chunks, int BN, int S_full, int S_t, long long total) {
+                                         int Cw, int CcB, int BN, long long total) {
   const long long idx = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
   if (idx >= total) return;
-  const int j = static_cast<int>(idx & 3);
-  long long r = idx >> 2;
-  const int n = static_cast<int>(r % BN);
-  r /= BN;
-  const int st = static_cast<int>(r % S_t);
-  const int nt = static_cast<int>(r / S_t);
-  int chunk = st / S_full;
-  if (chunk > n_chunks - 1) chunk = n_chunks - 1;
-  const int sic = st - chunk * S_full;
+  const int Kw = taps * Cw;
+  const int n = static_cast<int>(idx % BN);
+  long long r = idx / BN;
+  const int qg = static_cast<int>(r % Kw);
+  const int nt = static_cast<int>(r / Kw);
+  const int chunk_words = taps * CcB;
+  const int chunk = qg / chunk_words;
+  const int rem = qg - chunk * chunk_words;
   const int cc_this = min(CcB, Cw - chunk * CcB);
-  const int q = sic * 4 + j;
+  const int st = rem / kWS, j = rem - st * kWS;
+  const int nw = min(kWS, taps * cc_this - st * kWS);
+  const int tap = rem / cc_this, cwi = rem - tap * cc_this;
   const int c = nt * BN + n;
   uint32_t bytes[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (q < taps * cc_this && c < cout) {
-    const int tap = q / cc_this, cwi = q - tap * cc_this;
+  if (c < cout) {
     const uint32_t w = static_cast<uint32_t>(filter[(static_cast<long long>(c) * taps + tap) * Cw + chunk * CcB + cwi]);
     for (int kk = 0; kk < 32; ++kk) {
       const int s = kk >> 2, i = kk & 3;
@@ -248,7 +329,8 @@ __global__ void expand_weights_tc_kernel(const int32_t* __restrict__ filter, uin
       bytes[kk >> 2] |= (static_cast<uint32_t>(v) & 0xFFu) << (8 * (kk & 3));
     }
   }
-  uint8_t* dst = wt + (static_cast<long long>(nt) * S_t + st) * BN * 128 + (n >> 3) * 1024 + (2 * j) * 128 + (n & 7) * 16;
+  uint8_t* dst = wt + (static_cast<long long>(nt) * Kw + chunk * chunk_words + st * kWS) * BN * 32 +
+                 (n >> 3) * (nw * 256) + (2 * j) * 128 + (n & 7) * 16;
   *reinterpret_cast<uint4*>(dst) = make_uint4(bytes[0], bytes[1], bytes[2], bytes[3]);
   *reinterpret_cast<uint4*>(dst + 128) = make_uint4(bytes[4], bytes[5], bytes[6], bytes[7]);
 }
@@ -292,13 +374,14 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
   uint64_t* res_empty = res_full + kMaxNS;     // [kMaxNS]
 
   const int tid = threadIdx.x;
-  const int warp = tid >> 5, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);   // provably warp-uniform
+  const int lane = tid & 31;
 
   if (tid == 0) {
     for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < kNR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kNumExpWarps); }
     for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], kNumEpiWarps); }
     for (int i = 0; i < kMaxNS; ++i) { mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4); }
     fence_barrier_init();
   }
@@ -306,13 +389,16 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_base_p;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_base_p, 0);
   const uint32_t tmem_a = tmem + 256;
 
   const int n_items = p.n_tiles * p.m_tiles;
-  const int cwv_full = p.CcB / V;
-  const int cwv_last = (p.Cw - (p.n_chunks - 1) * p.CcB) / V;
-  constexpr int VPS = 4 / V;   // vectors per stage
+  const int cc_last = p.Cw - (p.n_chunks - 1) * p.CcB;   // words per pixel in the last channel chunk
+  constexpr int VPS = kWS / V;   // vectors per stage
+  constexpr int VPH = 4 / V;     // vectors per half stage (one tcgen05.st.x32)
+  const bool prof = LCE_TC_PROF != 0 && p.prof != nullptr && blockIdx.x == 0 && lane == 0;
+  long long pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  const long long prof_t0 = prof ? clock64() : 0;
 
   if (warp == 0) {
     // ===== activation producer =====
@@ -327,7 +413,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const long long wbase = halo_word_base(p, px_lo);
         for (int ch = 0; ch < p.n_chunks; ++ch, ++cnt) {
           const int rs = cnt % kNR;
-          mbar_wait_tc(&raw_empty[rs], ((cnt / kNR) & 1) ^ 1, 1);
+          mbar_wait_prof(&raw_empty[rs], ((cnt / kNR) & 1) ^ 1, 1, prof, pw[1]);
           unsigned char* dst = smem + p.off_raw + rs * p.raw_stage_bytes;
           if (p.mode_flat) {
             const int nwords = static_cast<int>((px_lo + px_cnt) * p.Cw - wbase);
@@ -345,72 +431,89 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc(p.BN);
-      const uint32_t stage_bytes = p.BN * 128;
-      uint32_t cntA = 0, cntB = 0, it = 0;
-      for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
-        const uint32_t ds = it & 1;
-        mbar_wait_tc(&d_empty[ds], ((it >> 1) & 1) ^ 1, 2);
-        tc_fence_after();
-        const uint32_t d_addr = tmem + ds * p.BN;
-        uint32_t first = 1;
-        int st_tile = 0;
-        for (int ch = 0; ch < p.n_chunks; ++ch) {
-          const int nq = p.taps * (ch == p.n_chunks - 1 ? p.Cw - ch * p.CcB : p.CcB);
-          const int nst = (nq + 3) >> 2;
-          for (int st = 0; st < nst; ++st, ++cntA, ++st_tile) {
-            const int as = cntA % kNA;
-            uint32_t bs;
-            if (p.b_resident) {
-              bs = st_tile;
-              mbar_wait_tc(&b_full[bs], 0, 3);
+    // ===== MMA issuer: the whole warp runs the loop (values stay in uniform registers), one
+    // elected lane issues =====
+    const uint32_t idesc = make_idesc(p.BN);
+    const uint32_t smem_base = smem_u32(smem);
+    const uint32_t row32 = static_cast<uint32_t>(p.BN) * 32u;      // bytes of one K word of a stage image
+    uint32_t as = 0, a_par = 0, bs = 0, b_par = 0, it = 0;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+      const uint32_t ds = it & 1;
+      mbar_wait_prof(&d_empty[ds], ((it >> 1) & 1) ^ 1, 2, prof, pw[1]);
+      tc_fence_after();
+      const uint32_t d_addr = tmem + ds * p.BN;
+      uint32_t acc = 0;
+      uint32_t wofs = 0;   // K-word offset of the stage inside the tile's weights (resident mode)
+      for (int ch = 0; ch < p.n_chunks; ++ch) {
+        const int nq = p.taps * (ch == p.n_chunks - 1 ? cc_last : p.CcB);
+        for (int q0 = 0; q0 < nq; q0 += kWS) {
+          const int nw = min(kWS, nq - q0);
+          uint32_t b_addr;
+          if (p.b_resident) {
+            b_addr = smem_base + wofs * row32;
+            if (it == 0) mbar_wait_prof(&b_full[bs], 0, 3, prof, pw[2]);
+          } else {
+            b_addr = smem_base + bs * (row32 * kWS);
+            mbar_wait_prof(&b_full[bs], b_par, 3, prof, pw[2]);
+          }
+          mbar_wait_prof(&a_full[as], a_par, 4, prof, pw[3]);
+          tc_fence_after();
+          const uint32_t lo = bdesc_lo(b_addr);
+          const uint32_t hi = bdesc_hi(static_cast<uint32_t>(nw) * 256u);
+          const uint32_t a_addr = tmem_a + as * 64;
+          if (elect_one()) {
+            if (nw == kWS) {
+#pragma unroll
+              for (int j = 0; j < kWS; ++j) mma_i8_ts2(d_addr, a_addr + j * 8, lo + j * 16, hi, idesc, j == 0 ? acc : 1u);
             } else {
-              bs = cntB % p.nB;
-              mbar_wait_tc(&b_full[bs], (cntB / p.nB) & 1, 3);
-            }
-            mbar_wait_tc(&a_full[as], (cntA / kNA) & 1, 4);
-            tc_fence_after();
-            const int nw = min(4, nq - st * 4);
-            const uint32_t b_addr = smem_u32(smem) + bs * stage_bytes;
-            for (int j = 0; j < nw; ++j) {
-              mma_i8_ts(d_addr, tmem_a + as * 32 + j * 8, make_bdesc(b_addr + j * 256), idesc, first ? 0u : 1u);
-              first = 0;
+              for (int j = 0; j < nw; ++j) mma_i8_ts2(d_addr, a_addr + j * 8, lo + j * 16, hi, idesc, j == 0 ? acc : 1u);
             }
             tc_commit(&a_empty[as]);
-            if (!p.b_resident) {
-              tc_commit(&b_empty[bs]);
-              ++cntB;
-            }
+            if (!p.b_resident) tc_commit(&b_empty[bs]);
+          }
+          __syncwarp();
+          acc = 1;
+          wofs += nw;
+          if (++as == kNA) { as = 0; a_par ^= 1; }
+          if (p.b_resident) {
+            ++bs;
+          } else if (++bs == static_cast<uint32_t>(p.nB)) {
+            bs = 0; b_par ^= 1;
           }
         }
-        tc_commit(&d_full[ds]);
       }
+      if (p.b_resident) bs = 0;
+      if (elect_one()) tc_commit(&d_full[ds]);
+      __syncwarp();
     }
   } else if (warp == 2) {
     // ===== weight producer =====
     if (lane == 0) {
-      const uint32_t stage_bytes = p.BN * 128;
-      if (p.b_resident) {
-        if (blockIdx.x < n_items) {
-          for (int st = 0; st < p.S_t; ++st) {
-            mbar_arrive_expect_tx(&b_full[st], stage_bytes);
-            bulk_g2s(smem + st * stage_bytes, p.wt + static_cast<size_t>(st) * stage_bytes, stage_bytes, &b_full[st]);
+      const uint32_t row32 = static_cast<uint32_t>(p.BN) * 32u;
+      uint32_t bs = 0, b_par = 0;
+      for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
+        const uint8_t* src = p.wt + static_cast<size_t>(nt) * p.Kw_total * row32;
+        uint32_t wofs = 0;
+        for (int ch = 0; ch < p.n_chunks; ++ch) {
+          const int nq = p.taps * (ch == p.n_chunks - 1 ? cc_last : p.CcB);
+          for (int q0 = 0; q0 < nq; q0 += kWS) {
+            const int nw = min(kWS, nq - q0);
+            const uint32_t bytes = static_cast<uint32_t>(nw) * row32;
+            if (p.b_resident) {
+              mbar_arrive_expect_tx(&b_full[bs], bytes);
+              bulk_g2s(smem + wofs * row32, src + static_cast<size_t>(wofs) * row32, bytes, &b_full[bs]);
+              ++bs;
+            } else {
+              mbar_wait_prof(&b_empty[bs], b_par ^ 1, 5, prof, pw[1]);
+              mbar_arrive_expect_tx(&b_full[bs], bytes);
+              bulk_g2s(smem + bs * (row32 * kWS), src + static_cast<size_t>(wofs) * row32, bytes, &b_full[bs]);
+              if (++bs == static_cast<uint32_t>(p.nB)) { bs = 0; b_par ^= 1; }
+            }
+            wofs += nw;
           }
         }
-      } else {
-        uint32_t cnt = 0;
-        for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
-          const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
-          const uint8_t* src = p.wt + static_cast<size_t>(nt) * p.S_t * stage_bytes;
-          for (int st = 0; st < p.S_t; ++st, ++cnt) {
-            const int bs = cnt % p.nB;
-            mbar_wait_tc(&b_empty[bs], ((cnt / p.nB) & 1) ^ 1, 5);
-            mbar_arrive_expect_tx(&b_full[bs], stage_bytes);
-            bulk_g2s(smem + bs * stage_bytes, src + static_cast<size_t>(st) * stage_bytes, stage_bytes, &b_full[bs]);
-          }
-        }
+        if (p.b_resident) break;   // loaded once, kept for every tile of this CTA
       }
     }
   } else if (warp == 3) {
@@ -424,7 +527,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const int n_cc = min(p.BN, p.cout - c_tile + 31) >> 5;
         for (int cc = 0; cc < n_cc; ++cc, ++cnt) {
           const int sl = cnt % p.nS;
-          mbar_wait_tc(&res_empty[sl], ((cnt / p.nS) & 1) ^ 1, 6);
+          mbar_wait_prof(&res_empty[sl], ((cnt / p.nS) & 1) ^ 1, 6, prof, pw[1]);
           mbar_arrive_expect_tx(&res_full[sl], kSlotBytes);
           tma_load_2d(smem + p.off_slots + sl * kSlotBytes, &tm_res, &res_full[sl], c_tile + cc * 32, static_cast<int>(m0));
         }
@@ -436,7 +539,18 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
     const int group = (warp - kFirstExpWarp) >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
+    const int pitch = p.mode_flat ? p.Cw : p.CcB;
     uint32_t cntA = 0, cntR = 0;
+    int pend_as = -1;   // stage whose tcgen05.st is in flight (its a_full arrive is still owed)
+    auto flush = [&]() {
+      if (pend_as >= 0) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&a_full[pend_as]);
+        pend_as = -1;
+      }
+    };
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
       const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
       const long long m0 = static_cast<long long>(item - nt * p.m_tiles) * kBM;
@@ -447,7 +561,6 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
       const long long m = m0 + row;
       const bool row_ok = m < p.M;
       int iy0 = 0, ix0 = 0, off0 = 0;
-      const int pitch = p.mode_flat ? p.Cw : p.CcB;
       if (row_ok) {
         const Pixel px = split_px(p, static_cast<uint32_t>(m));
         iy0 = px.oy * p.sh - p.ph;
@@ -458,57 +571,72 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
       for (int ch = 0; ch < p.n_chunks; ++ch, ++cntR) {
         const int rs = cntR % kNR;
         const bool last = ch == p.n_chunks - 1;
-        const int cwv = last ? cwv_last : cwv_full;
+        const int cwv = (last ? cc_last : p.CcB) / V;
         const FastDiv fd_cwv = last ? p.fd_cwv_last : p.fd_cwv_full;
         const int nvec = p.taps * cwv;
         const int nst = (nvec + VPS - 1) / VPS;
         const uint32_t* raw = reinterpret_cast<const uint32_t*>(smem + p.off_raw + rs * p.raw_stage_bytes);
-        mbar_wait_tc(&raw_full[rs], (cntR / kNR) & 1, 7);
+        mbar_wait_prof(&raw_full[rs], (cntR / kNR) & 1, 7, prof, pw[1]);
         for (int st = 0; st < nst; ++st, ++cntA) {
           if ((cntA & 1) != static_cast<uint32_t>(group)) continue;
           const int as = cntA % kNA;
           uint32_t v[32];
+          const long long tb0 = prof ? clock64() : 0;
           int kv = st * VPS;
           int tap = static_cast<int>(fdiv(static_cast<uint32_t>(kv), fd_cwv));
           int cv = kv - tap * cwv;
           int fy = static_cast<int>(fdiv(static_cast<uint32_t>(tap), p.fd_kw));
           int fx = tap - fy * p.KW;
+          auto build_half = [&]() {
 #pragma unroll
-          for (int u = 0; u < VPS; ++u) {
-            uint32_t w[V];
+            for (int u = 0; u < VPH; ++u, ++kv) {
+              uint32_t w[V];
 #pragma unroll
-            for (int e = 0; e < V; ++e) w[e] = 0;
-            const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
-            if (row_ok && kv + u < nvec && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
-                static_cast<unsigned>(ix) < static_cast<unsigned>(p.W))
-              load_words<V>(reinterpret_cast<const typename VecT<V>::T*>(raw + off0 + (fy * p.dh * p.W + fx * p.dw) * pitch + cv * V), w);
+              for (int e = 0; e < V; ++e) w[e] = 0;
+              const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
+              if (row_ok && kv < nvec && static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) &&
+                  static_cast<unsigned>(ix) < static_cast<unsigned>(p.W))
+                load_words<V>(reinterpret_cast<const typename VecT<V>::T*>(raw + off0 + (fy * p.dh * p.W + fx * p.dw) * pitch + cv * V), w);
 #pragma unroll
-            for (int e = 0; e < V; ++e) expand_word(w[e], &v[(u * V + e) * 8]);
-            if (++cv == cwv) {
-              cv = 0;
-              if (++fx == p.KW) { fx = 0; ++fy; }
+              for (int e = 0; e < V; ++e) expand_word(w[e], &v[(u * V + e) * 8]);
+              if (++cv == cwv) {
+                cv = 0;
+                if (++fx == p.KW) { fx = 0; ++fy; }
+              }
             }
-          }
-          mbar_wait_tc(&a_empty[as], ((cntA / kNA) & 1) ^ 1, 8);
+          };
+          build_half();
+          if (prof) pw[3] += clock64() - tb0;
+          flush();   // the previous stage's store has had this build to complete
+          mbar_wait_prof(&a_empty[as], ((cntA / kNA) & 1) ^ 1, 8, prof, pw[2]);
+          const long long ts0 = prof ? clock64() : 0;
           tc_fence_after();
-          tmem_st32(tmem_a + lane_base + as * 32, v);
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(&a_full[as]);
+          tmem_st32(tmem_a + lane_base + as * 64, v);
+          if (kv < nvec) {   // second half of the stage (absent in a short last stage)
+            build_half();
+            tmem_st32(tmem_a + lane_base + as * 64 + 32, v);
+          }
+          pend_as = as;
+          if (prof) { pw[4] += clock64() - ts0; pw[5] += 1; }
         }
+        flush();
         __syncwarp();
         if (lane == 0) mbar_arrive(&raw_empty[rs]);
       }
     }
+    flush();
   } else {
-    // ===== epilogue: thread = output pixel = TMEM lane =====
+    // ===== epilogue: thread = output pixel = TMEM lane; group g takes chunks cc with (cc & 1) == g
     const int q = warp & 3;
+    const int group = (warp - kFirstEpiWarp) >> 2;
+    const int etid = tid - kFirstEpiWarp * 32;     // 0..255
     const int row = q * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(q * 32) << 16;
     const float act_lo = p.residual_act == LCE_ACT_RELU_N1_TO_1 ? -1.0f : 0.0f;
     const float act_hi = p.residual_act == LCE_ACT_RELU ? __int_as_float(0x7f800000)
                                                         : (p.residual_act == LCE_ACT_RELU6 ? 6.0f : 1.0f);
     uint32_t it = 0, cntS = 0;
+    int pend_sl = -1;   // residual slot whose TMA store is still reading shared memory
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
       const long long m0 = static_cast<long long>(item - nt * p.m_tiles) * kBM;
@@ -517,24 +645,42 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
       const long long m = m0 + row;
       const bool row_ok = m < p.M;
       const uint32_t ds = it & 1;
-      // zero-padding: which taps of this pixel fall outside the image (reference.h:100-103)
+      // per-channel epilogue vectors of this n tile -> shared memory (once when there is one n tile)
+      int* tab = reinterpret_cast<int*>(smem + p.off_tab + (p.n_tiles > 1 ? (it & 1) * (kTabBytes / 2) : 0));
+      if (p.n_tiles > 1 || it == 0) {
+        if (etid < p.BN) {
+          const int c = c_tile + etid;
+          tab[etid] = p.wpop2[c];
+          if (OUT == LCE_OUT_BITPACKED) {
+            tab[384 + etid] = p.thr[c];
+          } else if (OUT != LCE_OUT_RAW_ACC) {
+            tab[128 + etid] = __float_as_int(p.mul[c]);
+            tab[256 + etid] = __float_as_int(p.bias[c]);
+          }
+        }
+        named_bar_sync(1, kNumEpiWarps * 32);
+      }
+      // zero padding: the taps of this pixel that need a correction
       unsigned long long oob = 0;
       if (p.tap_popc_t != nullptr && row_ok) {
         const Pixel px = split_px(p, static_cast<uint32_t>(m));
-        const int iy0 = px.oy * p.sh - p.ph, ix0 = px.ox * p.sw - p.pw;
-        for (int fy = 0; fy < p.KH; ++fy)
-          for (int fx = 0; fx < p.KW; ++fx) {
-            const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
-            if (!(static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)))
-              oob |= 1ull << (fy * p.KW + fx);
-          }
+        oob = zero_pad_tap_mask(p, px.oy, px.ox);
       }
-      mbar_wait_tc(&d_full[ds], (it >> 1) & 1, 9);
+      mbar_wait_prof(&d_full[ds], (it >> 1) & 1, 9, prof, pw[1]);
       tc_fence_after();
-      for (int cc = 0; cc < n_cc; ++cc) {
+      const int last_cc = ((n_cc - 1 - group) & ~1) + group;   // this group's last chunk (< group: none)
+      if (group >= n_cc) {   // nothing to read for this group in this tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&d_empty[ds]);
+      }
+      for (int cc = 0; cc < n_cc; ++cc, ++cntS) {
+        if ((cc & 1) != group) continue;
         uint32_t accu[32];
+        const long long tl0 = prof ? clock64() : 0;
         tmem_ld32(tmem + lane_base + ds * p.BN + cc * 32, accu);
-        if (cc == n_cc - 1) {
+        if (prof) { pw[3] += clock64() - tl0; pw[6] += 1; }
+        const long long tc0 = prof ? clock64() : 0;
+        if (cc == last_cc) {
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&d_empty[ds]);
@@ -544,13 +690,13 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         int x[32];
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
-          const int4 wp = __ldg(reinterpret_cast<const int4*>(p.wpop2 + c0) + k);
+          const int4 wp = reinterpret_cast<const int4*>(tab + cc * 32)[k];
           x[4 * k] = (static_cast<int>(accu[4 * k]) >> 2) + wp.x;
           x[4 * k + 1] = (static_cast<int>(accu[4 * k + 1]) >> 2) + wp.y;
           x[4 * k + 2] = (static_cast<int>(accu[4 * k + 2]) >> 2) + wp.z;
           x[4 * k + 3] = (static_cast<int>(accu[4 * k + 3]) >> 2) + wp.w;
         }
-        if (oob != 0) {
+        if (oob != 0 && !p.zp_float) {
           for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
             const int t = __ffsll(static_cast<long long>(mk)) - 1;
             const int4* tp = reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0);
@@ -567,7 +713,23 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         if (OUT == LCE_OUT_FLOAT || OUT == LCE_OUT_RAW_ACC) {
           const int sl = cntS % p.nS;
           unsigned char* buf = smem + p.off_slots + sl * kSlotBytes + q * 4096 + lane * 128;
-          if (OUT == LCE_OUT_FLOAT && p.has_res) mbar_wait_tc(&res_full[sl], (cntS / p.nS) & 1, 10);
+          const bool res = OUT == LCE_OUT_FLOAT && p.has_res;
+          // the store that last read a buffer of this warp must have finished reading it
+          if (lane == 0) {
+            if (res) {
+              if (pend_sl >= 0) {
+                tma_store_wait_read();
+                mbar_arrive(&res_empty[pend_sl]);
+              }
+            } else if (p.nS >= 4) {
+              tma_store_wait_read1();
+            } else {
+              tma_store_wait_read();
+            }
+          }
+          pend_sl = -1;
+          __syncwarp();
+          if (res) mbar_wait_prof(&res_full[sl], (cntS / p.nS) & 1, 10, prof, pw[2]);
           uint32_t bits = 0;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
@@ -575,12 +737,27 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             if (OUT == LCE_OUT_RAW_ACC) {
               *cell = make_uint4(x[4 * k] >> 1, x[4 * k + 1] >> 1, x[4 * k + 2] >> 1, x[4 * k + 3] >> 1);
             } else {
-              const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mul + c0) + k);
-              const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + k);
+              const float4 mu = reinterpret_cast<const float4*>(tab + 128 + cc * 32)[k];
+              const float4 bi = reinterpret_cast<const float4*>(tab + 256 + cc * 32)[k];
               float y0 = transform_float_x2(x[4 * k], p.clamp_min, p.clamp_max, mu.x, bi.x);
               float y1 = transform_float_x2(x[4 * k + 1], p.clamp_min, p.clamp_max, mu.y, bi.y);
               float y2 = transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z);
               float y3 = transform_float_x2(x[4 * k + 3], p.clamp_min, p.clamp_max, mu.w, bi.w);
+              if (oob != 0 && p.zp_float) {
+                // y += (-post_mul) * sum over the counted taps of (cin_pg - 2 popc(filter tap)): the
+                // float correction of zero_padding_correction.h:160-170,289-291 (mu is -post_mul)
+                int c0i = 0, c1i = 0, c2i = 0, c3i = 0;
+                for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
+                  const int t = __ffsll(static_cast<long long>(mk)) - 1;
+                  const int4 tv = __ldg(reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0) + k);
+                  c0i += p.cin_pg - 2 * tv.x; c1i += p.cin_pg - 2 * tv.y;
+                  c2i += p.cin_pg - 2 * tv.z; c3i += p.cin_pg - 2 * tv.w;
+                }
+                y0 = __fadd_rn(y0, __fmul_rn(mu.x, static_cast<float>(c0i)));
+                y1 = __fadd_rn(y1, __fmul_rn(mu.y, static_cast<float>(c1i)));
+                y2 = __fadd_rn(y2, __fmul_rn(mu.z, static_cast<float>(c2i)));
+                y3 = __fadd_rn(y3, __fmul_rn(mu.w, static_cast<float>(c3i)));
+              }
               if (p.has_res) {
                 const float4 rv = *reinterpret_cast<const float4*>(cell);
                 y0 = __fadd_rn(y0, rv.x); y1 = __fadd_rn(y1, rv.y); y2 = __fadd_rn(y2, rv.z); y3 = __fadd_rn(y3, rv.w);
@@ -593,26 +770,25 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
               bits |= ((y0 < 0.0f ? 1u : 0u) | (y1 < 0.0f ? 2u : 0u) | (y2 < 0.0f ? 4u : 0u) | (y3 < 0.0f ? 8u : 0u)) << (4 * k);
             }
           }
+          if (prof) pw[4] += clock64() - tc0;
+          const long long tq0 = prof ? clock64() : 0;
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
-            if (m0 + q * 32 < p.M) {
-              tma_store_2d(&tm_out, smem + p.off_slots + sl * kSlotBytes + q * 4096, c0, static_cast<int>(m0) + q * 32);
-              tma_store_wait_read();
-            }
-            if (OUT == LCE_OUT_FLOAT && p.has_res) mbar_arrive(&res_empty[sl]);
+            if (m0 + q * 32 < p.M) tma_store_2d(&tm_out, smem + p.off_slots + sl * kSlotBytes + q * 4096, c0, static_cast<int>(m0) + q * 32);
           }
+          if (res) pend_sl = sl;
           __syncwarp();
+          if (prof) pw[5] += clock64() - tq0;
           if (OUT == LCE_OUT_FLOAT && p.packed_out != nullptr && row_ok)
             p.packed_out[static_cast<size_t>(m) * p.cw_out + (c0 >> 5)] = static_cast<int32_t>(bits);
-          ++cntS;
         } else if (OUT == LCE_OUT_INT8) {
           if (row_ok) {
             uint32_t pk[8];
 #pragma unroll
             for (int k = 0; k < 8; ++k) {
-              const float4 mu = __ldg(reinterpret_cast<const float4*>(p.mul + c0) + k);
-              const float4 bi = __ldg(reinterpret_cast<const float4*>(p.bias + c0) + k);
+              const float4 mu = reinterpret_cast<const float4*>(tab + 128 + cc * 32)[k];
+              const float4 bi = reinterpret_cast<const float4*>(tab + 256 + cc * 32)[k];
               const int q0 = round_saturate_i8(transform_float_x2(x[4 * k], p.clamp_min, p.clamp_max, mu.x, bi.x));
               const int q1 = round_saturate_i8(transform_float_x2(x[4 * k + 1], p.clamp_min, p.clamp_max, mu.y, bi.y));
               const int q2 = round_saturate_i8(transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z));
@@ -633,7 +809,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
           uint32_t bits = 0;
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
-            const int4 th = __ldg(reinterpret_cast<const int4*>(p.thr + c0) + k);
+            const int4 th = reinterpret_cast<const int4*>(tab + 384 + cc * 32)[k];
             bits |= (((x[4 * k] >> 1) > th.x ? 1u : 0u) | ((x[4 * k + 1] >> 1) > th.y ? 2u : 0u) |
                      ((x[4 * k + 2] >> 1) > th.z ? 4u : 0u) | ((x[4 * k + 3] >> 1) > th.w ? 8u : 0u)) << (4 * k);
           }
@@ -643,9 +819,19 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
       }
     }
-    if (lane == 0) tma_store_wait_all();
+    if (lane == 0) {
+      if (pend_sl >= 0) {
+        tma_store_wait_read();
+        mbar_arrive(&res_empty[pend_sl]);
+      }
+      tma_store_wait_all();
+    }
   }
 
+  if (prof) {
+    pw[0] = clock64() - prof_t0;
+    for (int i = 0; i < 8; ++i) p.prof[warp * 8 + i] = pw[i];
+  }
   __syncwarp();
   tc_fence_before();
   __syncthreads();

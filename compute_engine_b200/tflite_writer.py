@@ -110,7 +110,8 @@ TENSOR_TYPE = {np.dtype(np.float32): 0, np.dtype(np.int32): 2, np.dtype(np.uint8
                np.dtype(np.int64): 4, np.dtype(np.bool_): 6, np.dtype(np.int8): 9}
 OP = {"ADD": 0, "AVERAGE_POOL_2D": 1, "CONV_2D": 3, "DEPTHWISE_CONV_2D": 4,
       "FULLY_CONNECTED": 9, "MAX_POOL_2D": 17, "MUL": 18, "RELU": 19, "RESHAPE": 22,
-      "SOFTMAX": 25, "MEAN": 40, "CUSTOM": 32, "CONCATENATION": 2, "PAD": 34, "PADV2": 60}
+      "SOFTMAX": 25, "MEAN": 40, "CUSTOM": 32, "CONCATENATION": 2, "PAD": 34, "PADV2": 60,
+      "DEQUANTIZE": 6}
 # BuiltinOptions union tags (schema_generated.h:1652-1694)
 OPT_TAG = {"CONV_2D": 1, "DEPTHWISE_CONV_2D": 2, "AVERAGE_POOL_2D": 5, "MAX_POOL_2D": 5,
            "FULLY_CONNECTED": 8, "SOFTMAX": 9, "ADD": 11, "MUL": 21, "RESHAPE": 17, "MEAN": 27,
@@ -235,3 +236,81 @@ class TFLiteModel:
                           3: ("o", fb.string(self.description)),
                           4: ("o", fb.offset_vector(buffers))})
         return fb.finish(model, b"TFL3")
+
+
+# --------------------------------------------------------------------------- #
+# FlexBuffers map of integers (the LCE ops' custom_options; format: SURVEY 9.2), in pure
+# Python so that a model can be serialised without loading any native library. Emits the same
+# bytes as csrc/host/flexbuffer_map.cc::WriteFlexIntMap (tests/test_host_ops.py compares them,
+# and both reproduce the blobs the real flatbuffers library wrote into
+# LCE/mlir/tests/legalize-lce.mlir:9,21).
+# --------------------------------------------------------------------------- #
+_FBT_INT, _FBT_MAP = 1, 9
+
+
+def flex_int_map(items: dict) -> bytes:
+    keys = list(items)
+    order = sorted(range(len(keys)), key=lambda i: keys[i].encode())
+    for log2w in range(3):
+        w = 1 << log2w
+        lim = 1 << (8 * w - 1)
+        out = bytearray()
+        key_pos = []
+        for k in keys:
+            key_pos.append(len(out))
+            out += k.encode() + b"\0"
+
+        def align():
+            while len(out) % w:
+                out.append(0)
+
+        def put(v):
+            out.extend(int(v & ((1 << (8 * w)) - 1)).to_bytes(w, "little"))
+
+        fits = True
+        align()
+        put(len(keys))
+        keys_vec = len(out)
+        for i in order:
+            off = len(out) - key_pos[i]
+            if off >= (1 << (8 * w)):
+                fits = False
+            put(off)
+        align()
+        put(len(out) - keys_vec)
+        put(w)
+        put(len(keys))
+        mp = len(out)
+        for i in order:
+            v = int(items[keys[i]])
+            if v >= lim or v < -lim:
+                fits = False
+            put(v)
+        for _ in keys:
+            out.append((_FBT_INT << 2) | log2w)
+        align()
+        if len(out) - mp >= (1 << (8 * w)):
+            fits = False
+        if not fits:
+            continue
+        put(len(out) - mp)
+        out.append((_FBT_MAP << 2) | log2w)
+        out.append(w)
+        return bytes(out)
+    raise ValueError("flexbuffer map does not fit 32-bit offsets")
+
+
+def bconv2d_options(channels_in, stride=(1, 1), dilation=(1, 1), padding=0, pad_values=1,
+                    activation=0) -> bytes:
+    """custom_options of LceBconv2d (keys as LCE/mlir/ir/lce_ops.cc:36-52)."""
+    return flex_int_map({"channels_in": channels_in, "dilation_height_factor": dilation[0],
+                         "dilation_width_factor": dilation[1],
+                         "fused_activation_function": activation, "pad_values": pad_values,
+                         "padding": padding, "stride_height": stride[0],
+                         "stride_width": stride[1]})
+
+
+def bmaxpool_options(filter_hw, stride_hw, padding) -> bytes:
+    return flex_int_map({"padding": padding, "stride_width": stride_hw[1],
+                         "stride_height": stride_hw[0], "filter_width": filter_hw[1],
+                         "filter_height": filter_hw[0]})

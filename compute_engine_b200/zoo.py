@@ -18,8 +18,23 @@ from __future__ import annotations
 
 import numpy as np
 
-from . import host as _host
-from .tflite_writer import TFLiteModel
+# Pure Python on purpose (numpy + the flatbuffer / flexbuffer writers of tflite_writer.py): no
+# native library is loaded, so bench.py's reference arm can synthesise the very same model bytes
+# by loading these two files alone (importlib, not the package).
+try:
+    from .tflite_writer import TFLiteModel, bconv2d_options
+except ImportError:      # loaded as a stand-alone file next to tflite_writer.py
+    from tflite_writer import TFLiteModel, bconv2d_options
+
+
+# Quantisation of an int8 image input (`input_type="int8"`): what the converter attaches to the
+# input tensor with inference_input_type=tf.int8; N(0,1) images span about +-4.
+INPUT_SCALE, INPUT_ZERO_POINT = 4.0 / 127.0, 0
+
+
+def quantize_images(x, scale=INPUT_SCALE, zero_point=INPUT_ZERO_POINT):
+    """float images -> the int8 tensor an int8-input model expects."""
+    return np.clip(np.rint(np.asarray(x, np.float32) / np.float32(scale)) + zero_point, -128, 127).astype(np.int8)
 
 
 class _Builder:
@@ -35,6 +50,21 @@ class _Builder:
 
     def act(self, shape, dtype=np.float32):
         return self.m.add_tensor(self._name("t"), shape, dtype)
+
+    def image_input(self, shape, input_type):
+        """The graph's input: float32 images, or int8 images + the DEQUANTIZE the converter
+        places behind an int8 input (then a step ships a quarter of the bytes to the device)."""
+        if input_type in ("float32", np.float32, None):
+            x = self.m.add_tensor("input", shape, np.float32)
+            self.m.inputs = [x]
+            return x
+        if input_type not in ("int8", np.int8):
+            raise ValueError(f"unsupported input_type {input_type!r}")
+        q = self.m.add_tensor("input", shape, np.int8, scale=INPUT_SCALE, zero_point=INPUT_ZERO_POINT)
+        self.m.inputs = [q]
+        x = self.act(shape)
+        self.m.add_op("DEQUANTIZE", [q], [x])
+        return x
 
     def const(self, data, dtype=np.float32, name="w"):
         return self.m.add_tensor(self._name(name), None, dtype, data=data)
@@ -122,7 +152,7 @@ class _Builder:
         oh, ow = -(-h // stride), -(-w // stride)
         y = self.act((b, oh, ow, cout))
         act_code = {"NONE": 0, "RELU": 1}[activation]
-        opts = _host.bconv2d_options(cin, (stride, stride), (1, 1), 0, pad_values, act_code)
+        opts = bconv2d_options(cin, (stride, stride), (1, 1), 0, pad_values, act_code)
         self.m.add_op("LceBconv2d",
                       [xq, self.const(filt, np.int32, "bfilter"), self.const(mul, name="pmul"),
                        self.const(t, name="pbias"), -1], [y], custom_options=opts)
@@ -146,12 +176,11 @@ class _Builder:
 
 
 def quicknet(batch=1, blocks=(4, 4, 4, 4), filters=(64, 128, 256, 512), seed=0, image=224,
-             name="QuickNet"):
+             name="QuickNet", input_type="float32"):
     """Returns the serialized .tflite bytes."""
     g = _Builder(seed, batch, name)
-    x = g.m.add_tensor("input", (batch, image, image, 3), np.float32)
-    g.m.inputs = [x]
     xs = (batch, image, image, 3)
+    x = g.image_input(xs, input_type)
     # stem
     x, xs = g.conv(x, xs, filters[0] // 4, 3, 2, activation="RELU")
     x, xs = g.depthwise(x, xs, 3, 2, bn=True)
@@ -170,15 +199,15 @@ def quicknet(batch=1, blocks=(4, 4, 4, 4), filters=(64, 128, 256, 512), seed=0, 
     return g.m.serialize()
 
 
-def quicknet_large(batch=1, seed=0):
-    return quicknet(batch, blocks=(6, 8, 12, 6), seed=seed, name="QuickNetLarge")
+def quicknet_large(batch=1, seed=0, image=224, input_type="float32"):
+    return quicknet(batch, blocks=(6, 8, 12, 6), seed=seed, image=image, name="QuickNetLarge",
+                    input_type=input_type)
 
 
-def birealnet18(batch=1, seed=0, image=224):
+def birealnet18(batch=1, seed=0, image=224, input_type="float32"):
     g = _Builder(seed, batch, "BiRealNet18")
-    x = g.m.add_tensor("input", (batch, image, image, 3), np.float32)
-    g.m.inputs = [x]
     xs = (batch, image, image, 3)
+    x = g.image_input(xs, input_type)
     x, xs = g.conv(x, xs, 64, 7, 2)
     x, xs = g.pool("MAX_POOL_2D", x, xs, 3, 2, "SAME")
     cin = 64

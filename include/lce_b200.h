@@ -94,6 +94,11 @@ int lce_b200_bconv2d_create(const lce_bconv2d_desc* d, const int32_t* filter,
                             const int32_t* thresholds, lce_b200_bconv2d** plan);
 int lce_b200_bconv2d_set_input_shape(lce_b200_bconv2d* plan, int batch,
                                      int in_h, int in_w);
+/* Which of the reference's two zero-padding results a plan reproduces (LCE_ZERO_PADDING_*,
+ * lce_b200_types.h). create() picks REFERENCE when channels_in is even (what
+ * Register_BCONV_2D_REF computes) and CORRECTION otherwise; the op shell sets it from the
+ * registration it was built through. No effect unless padding == SAME and pad_value == 0. */
+int lce_b200_bconv2d_set_zero_padding_mode(lce_b200_bconv2d* plan, int mode);
 int lce_b200_bconv2d_get_desc(const lce_b200_bconv2d* plan,
                               lce_bconv2d_desc* d, int* out_h, int* out_w);
 int lce_b200_bconv2d_run(lce_b200_bconv2d* plan, const int32_t* in_dev,

@@ -85,6 +85,13 @@ int lce_b200_f32_mean_hw(const float* in_dev, float* out_dev, int batch, int h, 
 int lce_b200_f32_softmax(const float* in_dev, float* out_dev, int64_t rows, int cols, float beta,
                          void* stream);
 
+/* DEQUANTIZE of an int8 (LCE_T_INT8) or uint8 (LCE_T_BOOL's code) tensor:
+ * out = float(scale * (q - zero_point)), TF/lite/kernels/internal/reference/dequantize.h:32-49.
+ * The entry of a graph whose input was converted with inference_input_type int8 / uint8: a step
+ * then ships a quarter of the bytes of float images over the host link. */
+int lce_b200_dequantize_affine(int in_type, const void* in_dev, float* out_dev, int64_t n,
+                               double scale, int32_t zero_point, void* stream);
+
 /* PAD / PADV2 (TF/lite/kernels/internal/reference/pad.h) of a 4-D tensor of 32-bit elements
  * (float32 or bitpacked int32 words): out dims = in + before + after, border = fill_bits. */
 int lce_b200_pad4d_32(const void* in_dev, void* out_dev, const int32_t* in_dims4,

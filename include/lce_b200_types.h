@@ -29,6 +29,16 @@ enum {
 };
 /* Output element type of LceBconv2d: dispatch of bconv2d.cc:551-564 */
 enum { LCE_OUT_FLOAT = 0, LCE_OUT_INT8 = 1, LCE_OUT_BITPACKED = 2 };
+/* SAME padding with pad_values == 0 ("zero padding"), the two results the reference has:
+ *  REFERENCE  : the reference kernel's integers (LCE/core/bconv2d/reference.h:76-77,100-103: an
+ *               out-of-bounds tap adds channels_in_per_group / 2), any output type, needs an
+ *               even channels_in (bconv2d.cc:188-200) -- Register_BCONV_2D_REF.
+ *  CORRECTION : the optimised kernels' result -- one-padding, OutputTransform, then a FLOAT
+ *               correction on the edge outputs (optimized_bgemm.h:153-177,
+ *               zero_padding_correction.h:39-299); float output without fused activation only --
+ *               Register_BCONV_2D (the reference's default) and ..._OPT_INDIRECT_BGEMM.
+ * The two differ by float rounding (up to ~1e5 ULP near cancellation). */
+enum { LCE_ZERO_PADDING_REFERENCE = 0, LCE_ZERO_PADDING_CORRECTION = 1 };
 /* Input element type of LceQuantize / output of LceDequantize
  * (quantization.cc:76-147) */
 enum { LCE_T_FLOAT = 0, LCE_T_INT8 = 1, LCE_T_BOOL = 2 };

@@ -259,6 +259,110 @@ int lce_oracle_bconv2d(const lce_bconv2d_desc* d, const int32_t* input,
                                thresholds, output);
 }
 
+/* --------------------------------------------------------------------------
+ * LceBconv2d with the OPTIMISED kernels' semantics (Register_BCONV_2D -- the
+ * reference's default registration -- and Register_BCONV_2D_OPT_INDIRECT_BGEMM).
+ * They produce the reference kernel's integers except under SAME padding with
+ * pad_values 0 ("zero padding"), float output: there the convolution runs with
+ * one-padding (out-of-bounds taps read as bit 0 = +1, optimized_bgemm.h:30-31,
+ * indirect_bgemm/kernel.h:101-174), the OutputTransform is applied, and a FLOAT
+ * correction is added to the edge outputs afterwards
+ * (optimized_bgemm.h:153-177 -> zero_padding_correction.h:178-299). Prepare only
+ * admits float output without a fused activation there (bconv2d.cc:188-200).
+ * -------------------------------------------------------------------------- */
+
+/* CacheCorrectionValues, zero_padding_correction.h:39-176, for one (case, y, x, out_c):
+ * -post_mul[c] * sum over the taps the case counts of (channels_in_pg - 2 popc(filter tap)). */
+static float zpc_cache_value(const lce_bconv2d_desc* d, const int32_t* filter,
+                             const float* post_mul, int direction, int y, int x,
+                             int out_c) {
+  const int cin_pg = d->channels_in / d->groups;
+  const int cw_pg = ceil_div(cin_pg, 32);
+  const int eff_w = (d->filter_w - 1) * d->dilation_w + 1;
+  const int eff_h = (d->filter_h - 1) * d->dilation_h + 1;
+  float correction = 0.0f;
+  for (int fy = 0; fy < d->filter_h; ++fy)
+    for (int fx = 0; fx < d->filter_w; ++fx) {
+      int popcount = 0;
+      const int32_t* f =
+          filter + (((size_t)out_c * d->filter_h + fy) * d->filter_w + fx) * cw_pg;
+      for (int w = 0; w < cw_pg; ++w) popcount += xor_popcount(f[w], 0);
+      const float cur = (float)(cin_pg - 2 * popcount);
+      const int efx = d->dilation_w * fx, efy = d->dilation_h * fy;
+      int counted;
+      switch (direction) {
+        case 0: counted = efy < y || efx < x; break;
+        case 1: counted = efy < y || (eff_w - efx) <= x; break;
+        case 2: counted = (eff_h - efy) <= y || efx < x; break;
+        default: counted = (eff_h - efy) <= y || (eff_w - efx) <= x; break;
+      }
+      if (counted) correction += cur;
+    }
+  const float mul = -1.0f * post_mul[out_c];
+  volatile float r = mul * correction;
+  return r;
+}
+
+/* ApplyCorrection, zero_padding_correction.h:178-299, restated literally (including its
+ * "cannot happen" fall-through for images smaller than the filter). */
+static void zpc_apply(const lce_bconv2d_desc* d, int out_h, int out_w,
+                      const int32_t* filter, const float* post_mul, float* output) {
+  const int eff_w = (d->filter_w - 1) * d->dilation_w + 1;
+  const int eff_h = (d->filter_h - 1) * d->dilation_h + 1;
+  const int left_off = ((out_w - 1) * d->stride_w + eff_w - d->in_w) / 2;
+  const int top_off = ((out_h - 1) * d->stride_h + eff_h - d->in_h) / 2;
+  const int C = d->channels_out;
+  for (int b = 0; b < d->batch; ++b)
+    for (int oy = 0; oy < out_h; ++oy) {
+      const int o_top = top_off - oy * d->stride_h;
+      const int o_bot = -o_top - d->in_h + eff_h;
+      for (int ox = 0; ox < out_w; ++ox) {
+        const int o_left = left_off - ox * d->stride_w;
+        const int o_right = -o_left - d->in_w + eff_w;
+        if (o_left <= 0 && o_right <= 0 && o_top <= 0 && o_bot <= 0) continue;
+        int cs, X, Y;
+        if (o_right <= 0 && o_top > 0 && o_bot < 0) {
+          cs = 0; X = o_left >= 0 ? o_left : 0; Y = o_top;
+        } else if (o_left < 0 && o_right > 0 && o_bot <= 0) {
+          cs = 1; X = o_right; Y = o_top >= 0 ? o_top : 0;
+        } else if (o_left > 0 && o_right < 0 && o_top <= 0) {
+          cs = 2; X = o_left; Y = o_bot >= 0 ? o_bot : 0;
+        } else if (o_left <= 0 && o_top < 0 && o_bot > 0) {
+          cs = 3; X = o_right >= 0 ? o_right : 0; Y = o_bot;
+        } else {
+          continue;
+        }
+        float* o = output + (((size_t)b * out_h + oy) * out_w + ox) * C;
+        for (int c = 0; c < C; ++c) {
+          volatile float sum = o[c] + zpc_cache_value(d, filter, post_mul, cs, Y, X, c);
+          o[c] = sum;
+        }
+      }
+    }
+}
+
+/* Returns 0, 1 on invalid parameters, 2 when Prepare would refuse (bconv2d.cc:188-200,
+ * optimised branch: zero padding needs float output and no fused activation). */
+int lce_oracle_bconv2d_opt_mt(const lce_bconv2d_desc* d, int threads,
+                              const int32_t* input, const int32_t* filter,
+                              const float* post_mul, const float* post_bias,
+                              const int32_t* thresholds, void* output) {
+  const int zero_padding = d->padding == LCE_PADDING_SAME && d->pad_value == 0;
+  if (!zero_padding)
+    return lce_oracle_bconv2d_mt(d, threads, input, filter, post_mul, post_bias,
+                                 thresholds, output);
+  if (!(d->out_type == LCE_OUT_FLOAT && d->activation == LCE_ACT_NONE)) return 2;
+  lce_bconv2d_desc one = *d;
+  one.pad_value = 1;
+  const int rc = lce_oracle_bconv2d_mt(&one, threads, input, filter, post_mul,
+                                       post_bias, thresholds, output);
+  if (rc) return rc;
+  int out_h, out_w, pad_h, pad_w;
+  if (lce_oracle_bconv2d_out_shape(d, &out_h, &out_w, &pad_h, &pad_w)) return 1;
+  zpc_apply(d, out_h, out_w, filter, post_mul, (float*)output);
+  return 0;
+}
+
 /* Portable BGEMM semantics: BGemmKernel<kStandardCpp>::Run,
  * LCE/core/bgemm/kernels.h:48-59 (float/int8) and :111-131 (bitpacked), with
  * the matrix orientation of optimized_bgemm.h:126-151: A = activations

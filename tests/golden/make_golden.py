@@ -84,7 +84,7 @@ def digest(a):
 def main():
     if L.load_ref() is None:
         sys.exit("oracle/_ref/liblce_ref.so missing: run `make -C oracle` here")
-    arrays, index = {}, {"bconv": [], "bconv_full": [], "quantize": [],
+    arrays, index = {}, {"bconv": [], "bconv_full": [], "bconv_zpc": [], "quantize": [],
                          "dequantize": [], "bmaxpool": []}
 
     for n, s in enumerate(bconv_specs()):
@@ -97,6 +97,25 @@ def main():
         key = f"bconv_{n}"
         arrays[key] = out
         index["bconv"].append({"key": key, "seed": seed, "spec": list(s)})
+
+    # Zero padding as the OPTIMISED kernels compute it -- what the reference's default
+    # registration returns: Kernel4x2Portable with one-padding, OutputTransform, then
+    # zero_padding_correction::ApplyCorrection (kind 1 of oracle/ref_shim.cc). Float output, no
+    # activation (bconv2d.cc:188-200), odd channel counts included.
+    for n, (b, h, w, c, fh, fw, co, st, dl) in enumerate([
+            (2, 8, 8, 64, 3, 3, 32, (1, 1), (1, 1)), (1, 16, 16, 128, 3, 3, 64, (2, 2), (1, 1)),
+            (2, 7, 7, 96, 3, 3, 16, (1, 1), (1, 1)), (1, 12, 12, 32, 5, 5, 8, (1, 1), (2, 2)),
+            (1, 9, 11, 64, 3, 3, 8, (2, 1), (1, 1)), (1, 5, 5, 33, 3, 3, 8, (1, 1), (1, 1)),
+            (1, 6, 6, 64, 5, 5, 8, (2, 2), (1, 1)), (3, 7, 7, 512, 3, 3, 64, (1, 1), (1, 1)),
+            (1, 14, 14, 256, 3, 3, 128, (2, 2), (1, 1)), (1, 10, 7, 100, 2, 3, 12, (1, 2), (1, 1))]):
+        seed = 5000 + n
+        case = L.make_bconv_case(seed, b, h, w, c, fh, fw, co, 1, st, dl, L.PADDING_SAME, 0,
+                                 L.ACT_NONE, L.OUT_FLOAT)
+        key = f"bconv_zpc_{n}"
+        arrays[key] = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, None,
+                                impl="ref", kind=1)
+        index["bconv_zpc"].append({"key": key, "seed": seed,
+                                   "spec": [b, h, w, c, fh, fw, co, list(st), list(dl)]})
 
     # config 1 (BASELINE.json configs[0]): 56x56x256 -> 256, k3 s1 SAME.
     # Outputs are 0.1-3.2 MB each, so only digests are stored.

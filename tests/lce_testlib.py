@@ -70,12 +70,59 @@ def load_oracle():
     return _cache["oracle"]
 
 
-def load_ref():
-    """The reference's own headers compiled by oracle/Makefile; None if absent."""
-    if "ref" not in _cache:
-        path = os.path.join(ORACLE_DIR, "_ref", "liblce_ref.so")
-        _cache["ref"] = C.CDLL(path) if os.path.exists(path) else None
-    return _cache["ref"]
+def _cpu_flags():
+    try:
+        with open("/proc/cpuinfo") as f:
+            for line in f:
+                if line.startswith("flags"):
+                    return set(line.split(":", 1)[1].split())
+    except OSError:
+        pass
+    return set()
+
+
+_V3 = {"avx", "avx2", "bmi1", "bmi2", "f16c", "fma", "abm", "movbe", "xsave"}
+_V4 = {"avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"}
+
+
+def ref_flavour(force=None):
+    """Widest x86-64 level of oracle/_ref the host can run: 'v4', 'v3' or 'base'
+    (LCE_REF_FLAVOUR overrides)."""
+    want = force or os.environ.get("LCE_REF_FLAVOUR")
+    if want:
+        return want
+    flags = _cpu_flags()
+    if _V3 <= flags and _V4 <= flags:
+        return "v4"
+    if _V3 <= flags:
+        return "v3"
+    return "base"
+
+
+def load_ref(flavour=None):
+    """The reference's own headers compiled by oracle/Makefile; None if absent. The widest
+    flavour the host CPU supports is picked unless `flavour` / LCE_REF_FLAVOUR says otherwise."""
+    fl = ref_flavour(flavour)
+    key = "ref" if flavour is None else "ref_" + fl
+    if key not in _cache:
+        lib = None
+        for cand in ([fl, "base"] if fl != "base" else ["base"]):
+            name = "liblce_ref.so" if cand == "base" else f"liblce_ref_{cand}.so"
+            path = os.path.join(ORACLE_DIR, "_ref", name)
+            if os.path.exists(path):
+                lib = C.CDLL(path)
+                _cache[key + "_name"] = name
+                break
+        _cache[key] = lib
+    return _cache[key]
+
+
+def ref_build_info():
+    load_ref()
+    return {"library": "oracle/_ref/" + str(_cache.get("ref_name")),
+            "flags": "-O3 -ffp-contract=off -mpopcnt -msse4.2" +
+                     {"liblce_ref_v3.so": " -march=x86-64-v3", "liblce_ref_v4.so": " -march=x86-64-v4"}.get(
+                         _cache.get("ref_name"), "")}
 
 
 def cdiv(a, b):
@@ -104,8 +151,10 @@ def out_shape(desc: BconvDesc, impl="oracle"):
 
 def bconv2d(desc: BconvDesc, inp, filt, mul=None, bias=None, thr=None,
             impl="oracle", kind=0, threads=1):
-    """Run LceBconv2d on the CPU checker. kind (ref only): 0 = BConv2DReference,
-    1 = indirect BGEMM (Kernel4x2Portable)."""
+    """Run LceBconv2d on the CPU checker. kind: 0 = the reference kernel's semantics
+    (BConv2DReference; Register_BCONV_2D_REF), 1 = the optimised kernels' (ref: indirect
+    BGEMM Kernel4x2Portable + zero_padding_correction; oracle: its restatement) -- they differ
+    only under zero padding, where kind 1 adds a FLOAT correction after the output transform."""
     lib = _lib(impl)
     oh, ow, _, _ = out_shape(desc, impl)
     if desc.out_type == OUT_BITPACKED:
@@ -117,9 +166,9 @@ def bconv2d(desc: BconvDesc, inp, filt, mul=None, bias=None, thr=None,
     inp = np.ascontiguousarray(inp, np.int32)
     filt = np.ascontiguousarray(filt, np.int32)
     if impl == "oracle":
-        rc = lib.lce_oracle_bconv2d_mt(C.byref(desc), C.c_int(threads), _ptr(inp),
-                                       _ptr(filt), _ptr(mul), _ptr(bias),
-                                       _ptr(thr), _ptr(out))
+        fn = lib.lce_oracle_bconv2d_opt_mt if kind == 1 else lib.lce_oracle_bconv2d_mt
+        rc = fn(C.byref(desc), C.c_int(threads), _ptr(inp), _ptr(filt), _ptr(mul),
+                _ptr(bias), _ptr(thr), _ptr(out))
     else:
         rc = lib.lce_ref_bconv2d_mt(C.byref(desc), C.c_int(kind),
                                     C.c_int(threads), _ptr(inp), _ptr(filt),

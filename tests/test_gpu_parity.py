@@ -123,6 +123,20 @@ def test_bconv_golden(capi, golden):
         assert_same_bits(run_gpu_bconv(capi, case), arrays[e["key"]], str(e["spec"]))
 
 
+def test_bconv_golden_zero_padding_correction(capi, golden):
+    """Vectors minted from the reference's optimised kernel + zero_padding_correction."""
+    index, arrays = golden
+    for e in index["bconv_zpc"]:
+        b, h, w, c, fh, fw, co, st, dl = e["spec"]
+        case = L.make_bconv_case(e["seed"], b, h, w, c, fh, fw, co, 1, tuple(st), tuple(dl),
+                                 L.PADDING_SAME, 0, L.ACT_NONE, L.OUT_FLOAT)
+        plan = capi.BConv2d(gpu_desc(capi, case.desc), case.filt, case.mul, case.bias)
+        plan.set_zero_padding_mode(1)
+        got = plan(dev(case.inp)).cpu().numpy()
+        plan.close()
+        assert_same_bits(got, arrays[e["key"]], str(e["spec"]))
+
+
 def test_bconv_config1_digests(capi, golden):
     """BASELINE.json configs[0]: 56x56x256 -> 256, k3 s1 SAME; digests minted from the
     reference's BConv2DReference (and equal to its indirect-BGEMM kernel for one-padding)."""
@@ -319,13 +333,29 @@ def test_bconv_fused_residual_and_pack_entry_point(capi):
         plan.close()
 
 
-@pytest.mark.parametrize("imma", ["0", "1"])
-def test_bconv_both_inner_products_vs_oracle(capi, imma, monkeypatch):
-    """The XOR+POPC kernel (LCE_B200_BCONV_IMMA=0) and the int8 tensor-pipe kernel (default where
-    a plan has full 64-channel tiles and float / raw output) produce the reference's integers:
-    ones / zero padding, stride, dilation, groups, multi-chunk K, ragged M, fused tail."""
+KERNEL_ENV = {"xor": {"LCE_B200_BCONV_TC": "0", "LCE_B200_BCONV_IMMA": "0"},
+              "imma": {"LCE_B200_BCONV_TC": "0", "LCE_B200_BCONV_IMMA": "1"},
+              "tc": {"LCE_B200_BCONV_TC": "1", "LCE_B200_BCONV_IMMA": "1"}}
+PATH_INDEX = {"tc": 0, "imma": 1, "xor": 2}
+
+
+def path_counts(capi):
     import ctypes as C
-    monkeypatch.setenv("LCE_B200_BCONV_IMMA", imma)
+    a = (C.c_uint64 * 3)()
+    capi.lib().lce_b200_path_counts(a)
+    return list(a)
+
+
+@pytest.mark.parametrize("imma", ["xor", "imma", "tc"])
+def test_bconv_both_inner_products_vs_oracle(capi, imma, monkeypatch):
+    """The three inner products -- XOR+POPC (north_star's), int8 mma.sync, and tcgen05 kind::i8
+    with TMEM accumulators (the default wherever a plan is eligible) -- produce the reference's
+    integers: ones / zero padding, stride, dilation, groups, multi-chunk K, ragged M, fused tail.
+    lce_b200_path_counts proves which kernel ran."""
+    import ctypes as C
+    for k, v in KERNEL_ENV[imma].items():
+        monkeypatch.setenv(k, v)
+    before = path_counts(capi)
     rng = np.random.default_rng(77)
     grid = [
         # b, h, w, cin, fh, fw, cout, groups, stride, dilation, padding, pad_value, act
@@ -342,7 +372,7 @@ def test_bconv_both_inner_products_vs_oracle(capi, imma, monkeypatch):
         case = L.make_bconv_case(9000 + n, b, h, w, cin, fh, fw, co, g, st, dl, pad, pv, act,
                                  L.OUT_FLOAT)
         want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr)
-        assert_same_bits(run_gpu_bconv(capi, case), want, f"imma={imma} case {n}")
+        assert_same_bits(run_gpu_bconv(capi, case), want, f"kernel={imma} case {n}")
         # fused tail on the same plan shape
         plan = capi.BConv2d(gpu_desc(capi, case.desc), case.filt, case.mul, case.bias)
         res = rng.standard_normal(want.shape).astype(np.float32)
@@ -359,9 +389,9 @@ def test_bconv_both_inner_products_vs_oracle(capi, imma, monkeypatch):
         ws = (want + res).astype(np.float32)
         if n % 2:
             ws = np.maximum(ws, 0)
-        assert_same_bits(out.cpu().numpy(), ws, f"imma={imma} fused sum {n}")
+        assert_same_bits(out.cpu().numpy(), ws, f"kernel={imma} fused sum {n}")
         if g == 1:
-            assert_same_bits(packed.cpu().numpy(), L.quantize(ws), f"imma={imma} fused signs {n}")
+            assert_same_bits(packed.cpu().numpy(), L.quantize(ws), f"kernel={imma} fused signs {n}")
         plan.close()
     # plain BGEMM, raw accumulators
     A = rng.integers(-2**31, 2**31 - 1, (333, 24), dtype=np.int64).astype(np.int32)
@@ -370,3 +400,86 @@ def test_bconv_both_inner_products_vs_oracle(capi, imma, monkeypatch):
     got = gemm(dev(A)).cpu().numpy()
     gemm.close()
     assert np.array_equal(got, L.bgemm(A, W, threads=4))
+    ran = [b - a for a, b in zip(before, path_counts(capi))]
+    # 8 plain + 8 fused convolutions + 1 BGEMM; the grouped case (2 launches) is outside the
+    # tcgen05 and (64-channel groups) inside the mma.sync kernel's reach
+    want_main = 17 if imma != "tc" else 15
+    assert ran[PATH_INDEX[imma]] == want_main, (imma, ran)
+    assert sum(ran) == 17, (imma, ran)
+
+
+# ---- zero padding: both results the reference has (include/lce_b200_types.h) ---------------- #
+BIREALNET_LAYERS = [  # (in hw, cin, cout, stride) of Bi-RealNet-18's 16 binary 3x3 convolutions
+    (56, 64, 64, 1), (56, 64, 64, 1), (56, 64, 64, 1), (56, 64, 64, 1),
+    (56, 64, 128, 2), (28, 128, 128, 1), (28, 128, 128, 1), (28, 128, 128, 1),
+    (28, 128, 256, 2), (14, 256, 256, 1), (14, 256, 256, 1), (14, 256, 256, 1),
+    (14, 256, 512, 2), (7, 512, 512, 1), (7, 512, 512, 1), (7, 512, 512, 1)]
+
+
+def ulp_distance(a, b):
+    ai = a.view(np.int32).astype(np.int64)
+    bi = b.view(np.int32).astype(np.int64)
+    ai = np.where(ai < 0, -(ai & 0x7FFFFFFF), ai)
+    bi = np.where(bi < 0, -(bi & 0x7FFFFFFF), bi)
+    return np.abs(ai - bi)
+
+
+@pytest.mark.parametrize("kernel", ["tc", "imma"])
+def test_zero_padding_matches_the_default_registration_within_1_ulp(capi, kernel, monkeypatch):
+    """Bi-RealNet-18's 16 layer shapes (SAME, pad_values 0, float output, no activation): the
+    result the reference's DEFAULT registration computes there is one-padding + OutputTransform +
+    the float correction of zero_padding_correction.h, not the reference kernel's integers (the
+    two differ by up to ~1e5 ULP near cancellation). north_star allows 1 ULP on the float
+    post-transform; LCE_ZERO_PADDING_CORRECTION reproduces the optimised kernels bit for bit
+    (0 ULP) -- against the reference's own headers compiled in oracle/_ref when that library
+    travelled with the snapshot, else against the oracle's restatement (pinned to it in
+    tests/test_oracle.py)."""
+    for k, v in KERNEL_ENV[kernel].items():
+        monkeypatch.setenv(k, v)
+    impl = "ref" if L.load_ref() is not None else "oracle"
+    worst = 0
+    for n, (hw, cin, cout, stride) in enumerate(BIREALNET_LAYERS):
+        case = L.make_bconv_case(4000 + n, 2, hw, hw, cin, 3, 3, cout, stride=(stride, stride),
+                                 pad_value=0, activation=L.ACT_NONE)
+        plan = capi.BConv2d(gpu_desc(capi, case.desc), case.filt, case.mul, case.bias)
+        plan.set_zero_padding_mode(1)
+        got = plan(dev(case.inp)).cpu().numpy()
+        want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, impl=impl, kind=1, threads=4)
+        worst = max(worst, int(ulp_distance(got, want).max()))
+        assert worst <= 1, (n, hw, cin, cout, stride, worst)
+        assert_same_bits(got, want, f"layer {n}")
+        # and the reference kernel's result on the same plan shape (Register_BCONV_2D_REF)
+        plan.set_zero_padding_mode(0)
+        got0 = plan(dev(case.inp)).cpu().numpy()
+        assert_same_bits(got0, L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, threads=4),
+                         f"layer {n} reference kernel")
+        plan.close()
+
+
+def test_zero_padding_correction_fused_tail_and_odd_channels(capi):
+    """CORRECTION mode with the fused shortcut + sign-pack tail (Bi-RealNet's residual block), and
+    an odd channels_in, which only the optimised kernels accept (bconv2d.cc:188-200)."""
+    import ctypes as C
+    rng = np.random.default_rng(9)
+    for (b, hw, cin, cout) in [(2, 14, 256, 256), (3, 7, 64, 64), (1, 9, 33, 32)]:
+        case = L.make_bconv_case(77 + cin, b, hw, hw, cin, 3, 3, cout, pad_value=0)
+        plan = capi.BConv2d(gpu_desc(capi, case.desc), case.filt, case.mul, case.bias)
+        plan.set_zero_padding_mode(1)
+        if cin % 2:
+            with pytest.raises(capi.LceError, match="Zero-padding is only supported"):
+                plan.set_zero_padding_mode(0)
+        res = rng.standard_normal((b, hw, hw, cout)).astype(np.float32)
+        out = torch.empty((b, hw, hw, cout), device="cuda")
+        packed = torch.empty((b, hw, hw, L.cdiv(cout, 32)), dtype=torch.int32, device="cuda")
+        d_in, d_res = dev(case.inp), dev(res)
+        rc = capi.lib().lce_b200_bconv2d_run_fused(
+            plan._h, C.c_void_p(d_in.data_ptr()), C.c_void_p(d_res.data_ptr()), C.c_int(L.ACT_NONE),
+            C.c_void_p(out.data_ptr()), C.c_void_p(packed.data_ptr()),
+            C.c_void_p(torch.cuda.current_stream().cuda_stream))
+        assert rc == 0, capi.lib().lce_b200_last_error()
+        torch.cuda.synchronize()
+        y = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, kind=1)
+        want = (y + res).astype(np.float32)
+        assert_same_bits(out.cpu().numpy(), want, "fused sum, float correction")
+        assert_same_bits(packed.cpu().numpy(), L.quantize(want), "fused signs, float correction")
+        plan.close()

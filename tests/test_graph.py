@@ -187,6 +187,56 @@ def test_gpu_interpreter_predict_true_batching():
     it.close()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("family", ["quicknet", "quicknet_large", "birealnet18"])
+def test_gpu_graph_parity_at_the_benched_shape(family):
+    """224 x 224 images, batch 64 -- the shape bench.py times (M up to 200 k pixels per layer,
+    thousands of tiles per binary convolution), not the 64 x 64 toys above:
+    (1) unfused graph: every LCE op, fed with the device's own input tensor, is bit exact on a
+        sample of images against the CPU checker;
+    (2) the FUSED graph under CUDA-graph replay (what is benchmarked) gives bit-identical class
+        probabilities for all 64 images;
+    (3) the sampled images' probabilities match the CPU graph to 2e-4."""
+    B, sel = 64, [0, 29, 63]
+    blob = zoo.MODELS[family](batch=1, image=224, seed=21)
+    m = R.parse(blob)
+    x = np.random.default_rng(8).standard_normal((B, 224, 224, 3)).astype(np.float32)
+    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    g.preserve_all_tensors(True)
+    g.resize_input(g.inputs()[0], x.shape)
+    g.allocate_tensors()
+    g.write(g.inputs()[0], x)
+    g.invoke()
+    n_lce = 0
+    for op in m["ops"]:
+        if op["code"] != 32:
+            continue
+        sub = {"tensors": m["tensors"], "ops": [op], "inputs": [op["inputs"][0]],
+               "outputs": [op["outputs"][0]]}
+        want, _ = R.run(sub, [g.read(op["inputs"][0])[sel]])
+        got = g.read(op["outputs"][0])[sel]
+        assert got.shape == want[0].shape
+        assert np.array_equal(got.view(np.uint8), want[0].view(np.uint8)), (op["custom"], n_lce)
+        n_lce += 1
+    assert n_lce >= 32
+    unfused = g.read(g.outputs()[0])
+    g.close()
+    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    assert g.fuse_all() > 0
+    g.resize_input(g.inputs()[0], x.shape)
+    g.allocate_tensors()
+    g.enable_cuda_graph(True)
+    for _ in range(3):                                   # eager, capture, replay
+        g.write(g.inputs()[0], x)
+        g.invoke()
+    fused = g.read(g.outputs()[0])
+    g.close()
+    assert np.array_equal(fused.view(np.uint8), unfused.view(np.uint8))
+    want_out, _ = R.run(m, [x[sel]])
+    assert np.abs(fused[sel] - want_out[0]).max() <= 2e-4
+    assert np.allclose(fused.sum(-1), 1.0, atol=1e-4)
+
+
 def test_residual_block_fusion_rewrites_the_graph():
     """Structure of the graph-level fusion (pure host logic; no device needed):
     LceBconv2d -> ADD [-> LceQuantize] collapses into one node."""

@@ -164,6 +164,53 @@ def test_golden_bconv_config1_digests(golden):
         assert hashlib.sha256(out.tobytes()).hexdigest() == e["sha256_reference_kernel"], e
 
 
+def zpc_case(e):
+    b, h, w, c, fh, fw, co, st, dl = e["spec"]
+    return L.make_bconv_case(e["seed"], b, h, w, c, fh, fw, co, 1, tuple(st), tuple(dl),
+                             L.PADDING_SAME, 0, L.ACT_NONE, L.OUT_FLOAT)
+
+
+def test_golden_zero_padding_correction(golden):
+    """The optimised kernels' zero padding (the reference's DEFAULT registration): the oracle's
+    restatement of zero_padding_correction.h equals the vectors minted from the reference's own
+    Kernel4x2Portable + ApplyCorrection, bit for bit; the reference kernel's integer result on the
+    same inputs differs (the two are different float computations), which is why both exist."""
+    index, arrays = golden
+    assert len(index["bconv_zpc"]) == 10
+    differs = 0
+    for e in index["bconv_zpc"]:
+        case = zpc_case(e)
+        out = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, None, kind=1)
+        want = arrays[e["key"]]
+        assert out.dtype == want.dtype and out.shape == want.shape, e
+        assert np.array_equal(out.view(np.uint8), want.view(np.uint8)), e
+        if case.desc.channels_in % 2 == 0:
+            ref_kernel = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, None, kind=0)
+            assert np.allclose(ref_kernel, want, rtol=1e-3, atol=1e-3)      # bconv2d_test.cc:396-405
+            differs += int(not np.array_equal(ref_kernel.view(np.uint8), want.view(np.uint8)))
+    assert differs > 0
+    # config 1 with zero padding: the committed digest of the reference's optimised kernel
+    for e in index["bconv_full"]:
+        if e["pad_value"] == 0 and "sha256_indirect_kernel" in e:
+            case = L.make_bconv_case(e["seed"], 1, 56, 56, 256, 3, 3, 256, 1, (1, 1), (1, 1),
+                                     L.PADDING_SAME, 0, e["activation"], e["out_type"])
+            out = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, None, kind=1)
+            assert hashlib.sha256(out.tobytes()).hexdigest() == e["sha256_indirect_kernel"], e
+
+
+def test_optimised_semantics_refusals():
+    """bconv2d.cc:188-200, optimised branch: zero padding needs float output, no activation."""
+    for act, ot in ((L.ACT_RELU, L.OUT_FLOAT), (L.ACT_NONE, L.OUT_INT8), (L.ACT_NONE, L.OUT_BITPACKED)):
+        case = L.make_bconv_case(1, 1, 6, 6, 64, 3, 3, 8, pad_value=0, activation=act, out_type=ot)
+        with pytest.raises(ValueError):
+            L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr, kind=1)
+    # everywhere else the optimised kernels compute the reference kernel's integers
+    case = L.make_bconv_case(2, 2, 7, 5, 96, 3, 2, 24, pad_value=1, activation=L.ACT_RELU)
+    a = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, None, kind=1)
+    b = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, None, kind=0)
+    assert np.array_equal(a.view(np.uint8), b.view(np.uint8))
+
+
 def test_golden_quantize_dequantize_bmaxpool(golden):
     index, arrays = golden
     for e in index["quantize"]:
@@ -205,6 +252,13 @@ def test_live_reference_random_walk():
         b = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr,
                       impl="ref", kind=0)
         assert np.array_equal(a.view(np.uint8), b.view(np.uint8)), L.desc_to_dict(case.desc)
+        # the optimised kernels (indirect BGEMM + float zero-padding correction) where legal
+        if g == 1 and not (pad == L.PADDING_SAME and pv == 0 and
+                           (ot != L.OUT_FLOAT or act != L.ACT_NONE)):
+            a1 = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr, kind=1)
+            b1 = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr,
+                           impl="ref", kind=1)
+            assert np.array_equal(a1.view(np.uint8), b1.view(np.uint8)), L.desc_to_dict(case.desc)
 
 
 def test_oracle_bgemm_equals_1x1_bconv():

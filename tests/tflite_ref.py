@@ -189,7 +189,7 @@ def _pool(x, o, is_max):
     return _act(y, act).permute(0, 2, 3, 1).contiguous().numpy()
 
 
-def run(model, inputs, threads=8, lce_impl="oracle", bconv_kind=0):
+def run(model, inputs, threads=8, lce_impl="oracle", bconv_kind=1):
     """Execute the parsed model on the CPU. `inputs`: list of arrays (any batch)."""
     vals = {}
     for i, t in enumerate(model["tensors"]):
@@ -259,6 +259,10 @@ def run(model, inputs, threads=8, lce_impl="oracle", bconv_kind=0):
             pads = np.asarray(ins[1]).reshape(-1, 2)
             fill = ins[2].reshape(()) if len(ins) > 2 and ins[2] is not None else 0
             out = np.pad(ins[0], [(int(a), int(b)) for a, b in pads], constant_values=fill)
+        elif code == 6:              # DEQUANTIZE (reference/dequantize.h:32-49: the product in double)
+            it = model["tensors"][op["inputs"][0]]
+            out = (np.float64(np.float32(it["scale"])) *
+                   (ins[0].astype(np.int64) - int(it["zero_point"])).astype(np.float64)).astype(np.float32)
         elif code == 2:              # CONCATENATION
             out = np.concatenate(ins, axis=o.scalar(0, "i"))
         else:

@@ -109,7 +109,7 @@ def bgemm_case(M, N, K_bits, out_type=L.OUT_RAW_ACC, seed=0, oracle=True):
 
 
 def conv_case(seed, b, hw, cin, k, cout, out_type=L.OUT_FLOAT, stride=1, dil=1, padding=L.PADDING_SAME,
-              pad_value=1, act=L.ACT_NONE, oracle=True):
+              pad_value=1, act=L.ACT_NONE, oracle=True, zp_mode=0):
     case = L.make_bconv_case(seed, b, hw, hw, cin, k, k, cout, stride=(stride, stride), dilation=(dil, dil),
                              padding=padding, pad_value=pad_value, activation=act, out_type=out_type)
     x = torch.from_numpy(case.inp).cuda()
@@ -118,19 +118,20 @@ def conv_case(seed, b, hw, cin, k, cout, out_type=L.OUT_FLOAT, stride=1, dil=1, 
         set_tc(on)
         d = capi.BconvDesc(*[getattr(case.desc, n) for n, _ in case.desc._fields_])
         plan = capi.BConv2d(d, case.filt, case.mul, case.bias, case.thr)
+        plan.set_zero_padding_mode(zp_mode)
         p0 = paths()
         out = plan(x)
         wd = watchdog()
         p1 = paths()
         res[on] = (out.cpu().numpy(), [b_ - a for a, b_ in zip(p0, p1)], wd, timeit(lambda: plan(x)))
         plan.close()
-    name = f"conv b={b} hw={hw} cin={cin} k={k} cout={cout} out={out_type} s={stride} d={dil} pad={padding}/{pad_value} act={act}"
+    name = f"conv zp={zp_mode} b={b} hw={hw} cin={cin} k={k} cout={cout} out={out_type} s={stride} d={dil} pad={padding}/{pad_value} act={act}"
     got, path, wd, t_tc = res[True]
     base, _, _, t_old = res[False]
     ok = path[0] == 1 and wd is None and np.array_equal(got.view(np.uint8), base.view(np.uint8))
     extra = f"path={path} wd={wd} t_tc={t_tc*1e3:.1f}us t_old={t_old*1e3:.1f}us"
     if oracle and got.size * k * k * cin <= 4e9:
-        want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr, threads=32)
+        want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr, threads=32, kind=zp_mode)
         ok_o = np.array_equal(got.view(np.uint8), want.view(np.uint8))
         extra += f" oracle={'eq' if ok_o else 'DIFF'}"
         ok = ok and ok_o
@@ -200,6 +201,10 @@ def main():
         conv_case(4, 5, 7, 512, 3, 512)
         conv_case(5, 2, 16, 128, 3, 128, pad_value=0)        # zero-padding correction
         conv_case(6, 2, 16, 64, 3, 128, stride=2, pad_value=0)
+        conv_case(5, 2, 16, 128, 3, 128, pad_value=0, zp_mode=1)   # the optimised kernels' float correction
+        conv_case(6, 2, 16, 64, 3, 128, stride=2, pad_value=0, zp_mode=1)
+        conv_case(12, 3, 7, 96, 3, 64, pad_value=0, zp_mode=1)
+        conv_case(13, 1, 12, 32, 5, 32, dil=2, pad_value=0, zp_mode=1)
         conv_case(7, 2, 12, 32, 5, 64, dil=2)                # Cw = 1
         conv_case(8, 2, 12, 96, 3, 64, padding=L.PADDING_VALID)
         conv_case(9, 2, 9, 128, 1, 128)

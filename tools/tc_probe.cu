@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(128) probe_mma(const int8_t* __restrict__ A_im
 }
 
 // ------------------------------------------------------------------ T4: issue rate
-__global__ void __launch_bounds__(128) probe_rate(int mode, int N, int iters, long long* cycles) {
+__global__ void __launch_bounds__(128) probe_rate(int mode, int N, int iters, long long* cycles, int alt) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -191,8 +191,9 @@ __global__ void __launch_bounds__(128) probe_rate(int mode, int N, int iters, lo
     for (int it = 0; it < iters; ++it) {
       const int ks = it & 3;
       const uint64_t bd = make_sdesc(Bs + ks * 256, 128, 1024, 0);
-      if (mode == 0) mma_i8_ss(tb + (it & 1) * 256 * 0, make_sdesc(As + ks * 256, 128, 1024, 0), bd, idesc, 1);
-      else mma_i8_ts(tb, tb + 256 + ks * 8, bd, idesc, 1);
+      const uint32_t dd = tb + (alt ? (it % alt) * N : 0);   // alt independent accumulators (alt * N <= 256)
+      if (mode == 0) mma_i8_ss(dd, make_sdesc(As + ks * 256, 128, 1024, 0), bd, idesc, 1);
+      else mma_i8_ts(dd, tb + 256 + ks * 8, bd, idesc, 1);
     }
     tc_commit(&bar);
   }
@@ -425,15 +426,17 @@ int main() {
     long long* dc;
     CK(cudaMalloc(&dc, 148 * 8));
     CK(cudaFuncSetAttribute(probe_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int alt : {0, 2, 4})
     for (int mode = 0; mode < 2; ++mode)
-      for (int N : {64, 128, 256}) {
+      for (int N : {32, 64, 128, 256}) {
+        if (alt * N > 256) continue;
         const int iters = 8192;
         cudaEvent_t e0, e1;
         cudaEventCreate(&e0); cudaEventCreate(&e1);
-        probe_rate<<<148, 128, (128 + 256) * 128>>>(mode, N, 64, dc);
+        probe_rate<<<148, 128, (128 + 256) * 128>>>(mode, N, 64, dc, alt);
         CK(cudaDeviceSynchronize());
         cudaEventRecord(e0);
-        probe_rate<<<148, 128, (128 + 256) * 128>>>(mode, N, iters, dc);
+        probe_rate<<<148, 128, (128 + 256) * 128>>>(mode, N, iters, dc, alt);
         cudaEventRecord(e1);
         CK(cudaDeviceSynchronize());
         float ms;
@@ -441,7 +444,7 @@ int main() {
         std::vector<long long> c(148);
         CK(cudaMemcpy(c.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
         const double macs = 148.0 * iters * 128.0 * N * 32.0;
-        printf("  mode=%s N=%3d: %.3f ms, %.1f cycles/MMA (SM0), %.0f MAC/clk/SM, %.1f int8 TOP/s\n", mode ? "TS" : "SS", N, ms,
+        printf("  alt=%d mode=%s N=%3d: %.3f ms, %.1f cycles/MMA (SM0), %.0f MAC/clk/SM, %.1f int8 TOP/s\n", alt, mode ? "TS" : "SS", N, ms,
                static_cast<double>(c[0]) / iters, 128.0 * N * 32.0 * iters / static_cast<double>(c[0]), 2.0 * macs / (ms * 1e-3) / 1e12);
       }
     cudaFree(dc);
