@@ -2,6 +2,8 @@
 // Python front-end and the tests drive it through ctypes). Mirrors the calls a
 // C++ user of the reference makes in examples/lce_minimal.cc:31-53:
 //   resolver + RegisterLCECustomOps -> build graph -> AllocateTensors -> Invoke.
+#include <cuda_runtime.h>
+
 #include <cstring>
 #include <string>
 #include <vector>
@@ -17,20 +19,25 @@ namespace lce_b200 {
 void RegisterBuiltinOps(OpResolver* resolver);  // builtin_ops.cc
 bool BuildGraphFromTflite(const uint8_t* data, size_t size, const OpResolver& resolver,
                           Graph* graph);        // tflite_model.cc
-OpResolver* DefaultResolver() {
-  static OpResolver* r = [] {
+// One resolver per selector of RegisterLCECustomOps (lce_ops_register.h:25-53):
+// 0 = default, 1 = use_reference_bconv, 2 = use_indirect_bgemm.
+OpResolver* Resolver(int which) {
+  static OpResolver* r[3] = {nullptr, nullptr, nullptr};
+  if (which < 0 || which > 2) which = 0;
+  if (!r[which]) {
     auto* res = new OpResolver();
-    compute_engine::tflite::RegisterLCECustomOps(res);
+    compute_engine::tflite::RegisterLCECustomOps(res, which == 1, which == 2);
     // the reference's other registrations stay reachable under explicit names
     res->AddCustom("LceBconv2d:REF", compute_engine::tflite::Register_BCONV_2D_REF());
     res->AddCustom("LceBconv2d:OPT_BGEMM", compute_engine::tflite::Register_BCONV_2D_OPT_BGEMM());
     res->AddCustom("LceBconv2d:OPT_INDIRECT_BGEMM",
                    compute_engine::tflite::Register_BCONV_2D_OPT_INDIRECT_BGEMM());
     RegisterBuiltinOps(res);
-    return res;
-  }();
-  return r;
+    r[which] = res;
+  }
+  return r[which];
 }
+OpResolver* DefaultResolver() { return Resolver(0); }
 }  // namespace lce_b200
 
 extern "C" {
@@ -55,10 +62,44 @@ void* lce_host_graph_from_tflite(const uint8_t* data, size_t size, int device_ar
   return g;
 }
 
+// The same with the selectors of RegisterLCECustomOps / the reference's Interpreter
+// (LCE/tflite/python/interpreter.py:40-58): use_reference_bconv resolves LceBconv2d to
+// Register_BCONV_2D_REF, use_indirect_bgemm to Register_BCONV_2D_OPT_INDIRECT_BGEMM.
+void* lce_host_graph_from_tflite_ex(const uint8_t* data, size_t size, int device_arena,
+                                    int use_reference_bconv, int use_indirect_bgemm,
+                                    const char** error) {
+  static thread_local std::string msg;
+  auto* g = new Graph(device_arena != 0);
+  const int which = use_reference_bconv ? 1 : (use_indirect_bgemm ? 2 : 0);
+  if (!lce_b200::BuildGraphFromTflite(data, size, *lce_b200::Resolver(which), g)) {
+    msg = g->last_error();
+    if (error) *error = msg.c_str();
+    delete g;
+    return nullptr;
+  }
+  return g;
+}
+
+// Device selection for processes that drive several GPUs (one graph per device).
+int lce_host_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+int lce_host_set_device(int index) { return cudaSetDevice(index) == cudaSuccess ? 0 : 1; }
+int lce_host_get_device(void) {
+  int d = -1;
+  if (cudaGetDevice(&d) != cudaSuccess) cudaGetLastError();
+  return d;
+}
+
 // Make an external registration (e.g. the oracle-backed CPU ops used by the CPU
 // tests) available under `name`.
 void lce_host_register_custom(const char* name, const TfLiteRegistration* registration) {
-  lce_b200::DefaultResolver()->AddCustom(name, registration);
+  for (int w = 0; w < 3; ++w) lce_b200::Resolver(w)->AddCustom(name, registration);
 }
 int lce_host_has_custom(const char* name) {
   return lce_b200::DefaultResolver()->FindCustom(name) != nullptr;

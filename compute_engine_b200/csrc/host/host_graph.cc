@@ -297,7 +297,7 @@ TfLiteStatus Graph::PlanArena() {
   return kTfLiteOk;
 }
 
-extern "C" TfLiteRegistration* lce_b200_internal_Register_BCONV_2D_FUSED(void);
+extern "C" TfLiteRegistration* lce_b200_internal_Register_BCONV_2D_FUSED(const TfLiteRegistration* original);
 
 int Graph::FuseResidualBlocks() {
   if (!device_arena_) return 0;
@@ -317,6 +317,8 @@ int Graph::FuseResidualBlocks() {
   for (size_t i = 0; i < nodes_.size(); ++i) {
     NodeRecord& b = *nodes_[i];
     if (b.name != "LceBconv2d" || b.initialized || b.node.inputs->size != 5) continue;
+    TfLiteRegistration* fused_reg = lce_b200_internal_Register_BCONV_2D_FUSED(b.registration);
+    if (fused_reg == nullptr) continue;   // a foreign "LceBconv2d" (e.g. the CPU test double)
     const int y = b.node.outputs->data[0];
     if (tensors_[y].type != kTfLiteFloat32 || is_graph_output(y)) continue;
     std::vector<size_t> cy = consumers(y);
@@ -328,6 +330,20 @@ int Graph::FuseResidualBlocks() {
     if (in0 == in1) continue;
     const int r = in0 == y ? in1 : in0;
     if (tensors_[r].type != kTfLiteFloat32 || tensors_[r].allocation_type == kTfLiteMmapRo) continue;
+    // Preconditions of the fused kernel, checked before the graph is rewritten (both graphs below
+    // run correctly unfused): the shortcut has exactly the convolution's shape (ADD would also
+    // accept a broadcast over the last dimension), and the convolution is not grouped (the fused
+    // sign-pack needs groups == 1): filter words per pixel == input words per pixel.
+    {
+      const TfLiteIntArray* ys = tensors_[y].dims;
+      const TfLiteIntArray* rs = tensors_[r].dims;
+      bool same = ys && rs && ys->size == rs->size;
+      for (int k = 0; same && k < ys->size; ++k) same = ys->data[k] == rs->data[k];
+      if (!same) continue;
+      const TfLiteIntArray* xs = tensors_[b.node.inputs->data[0]].dims;
+      const TfLiteIntArray* fs = tensors_[b.node.inputs->data[1]].dims;
+      if (!xs || !fs || xs->size != 4 || fs->size != 4 || xs->data[3] != fs->data[3]) continue;
+    }
     // the shortcut must already exist when the bconv runs
     bool r_ready = std::find(inputs_.begin(), inputs_.end(), r) != inputs_.end();
     for (size_t k = 0; k < i && !r_ready; ++k)
@@ -358,7 +374,7 @@ int Graph::FuseResidualBlocks() {
     LceB200IntArrayFree(b.node.outputs);
     b.node.inputs = MakeDims(ins);
     b.node.outputs = MakeDims(outs);
-    b.registration = lce_b200_internal_Register_BCONV_2D_FUSED();
+    b.registration = fused_reg;
     b.builtin_blob.assign(reinterpret_cast<const uint8_t*>(&add_act),
                           reinterpret_cast<const uint8_t*>(&add_act) + 4);
     b.node.builtin_data = b.builtin_blob.data();

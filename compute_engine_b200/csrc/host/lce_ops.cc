@@ -24,7 +24,9 @@
 
 namespace {
 
-void* g_stream = nullptr;
+// The stream the ops launch on: set by the graph host before it walks its nodes. Thread local:
+// two graphs invoked from two threads (one Interpreter per device) do not see each other's.
+thread_local void* g_stream = nullptr;
 
 #define LCE_ENSURE(ctx, cond)                                                          \
   do {                                                                                 \
@@ -585,9 +587,9 @@ TfLiteStatus BMaxPoolEval(TfLiteContext* context, TfLiteNode* node) {
                       });
 }
 
+template <KernelType kt>
 TfLiteRegistration* BconvFusedRegistration() {
-  static TfLiteRegistration r = {BconvInit, BconvFree, BconvPrepare<KernelType::kCuda, true>,
-                                 BconvFusedEval};
+  static TfLiteRegistration r = {BconvInit, BconvFree, BconvPrepare<kt, true>, BconvFusedEval};
   return &r;
 }
 
@@ -612,7 +614,18 @@ void LceB200IntArrayFree(TfLiteIntArray* a) { free(a); }
 #endif
 
 // host-internal: the fused residual-block node created by Graph::FuseResidualBlocks
-TfLiteRegistration* lce_b200_internal_Register_BCONV_2D_FUSED(void) { return BconvFusedRegistration(); }
+// The fused node keeps the validation rules and zero-padding result of the registration the
+// LceBconv2d node was resolved to (nullptr: not one of this library's LceBconv2d registrations).
+TfLiteRegistration* lce_b200_internal_Register_BCONV_2D_FUSED(const TfLiteRegistration* original) {
+  if (original == BconvRegistration<KernelType::kCuda>()) return BconvFusedRegistration<KernelType::kCuda>();
+  if (original == BconvRegistration<KernelType::kReference>())
+    return BconvFusedRegistration<KernelType::kReference>();
+  if (original == BconvRegistration<KernelType::kOptimizedBGEMM>())
+    return BconvFusedRegistration<KernelType::kOptimizedBGEMM>();
+  if (original == BconvRegistration<KernelType::kOptimizedIndirectBGEMM>())
+    return BconvFusedRegistration<KernelType::kOptimizedIndirectBGEMM>();
+  return nullptr;
+}
 
 void lce_b200_set_stream(void* stream) { g_stream = stream; }
 void* lce_b200_get_stream(void) { return g_stream; }

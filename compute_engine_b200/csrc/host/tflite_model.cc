@@ -126,6 +126,44 @@ bool BuildGraphFromTflite(const uint8_t* data, size_t size, const OpResolver& re
   Table sg = model.elem_table(subgraphs, 0);
   Vec tensors = sg.vec(0, 4), ops = sg.vec(3, 4);
   Vec inputs = sg.vec(1, 4), outputs = sg.vec(2, 4);
+  // Every tensor index the file carries is checked HERE, once: the op shells and the fusion
+  // passes index context->tensors with them without further checks. Operator inputs may be -1
+  // (kTfLiteOptionalTensor); operator outputs and the graph's inputs / outputs may not.
+  if (!tensors.b || !ops.b) {
+    graph->set_error("subgraph without a tensors or operators vector");
+    return false;
+  }
+  auto index_ok = [&](int32_t t, bool optional) {
+    return (optional && t == -1) || (t >= 0 && static_cast<uint32_t>(t) < tensors.len);
+  };
+  for (uint32_t k = 0; k < inputs.len; ++k)
+    if (!index_ok(inputs.at<int32_t>(k), false)) {
+      graph->set_error("graph input refers to a missing tensor");
+      return false;
+    }
+  for (uint32_t k = 0; k < outputs.len; ++k)
+    if (!index_ok(outputs.at<int32_t>(k), false)) {
+      graph->set_error("graph output refers to a missing tensor");
+      return false;
+    }
+  for (uint32_t i = 0; i < ops.len; ++i) {
+    Table op = sg.elem_table(ops, i);
+    if (op.scalar<uint32_t>(0, 0) >= codes.len) {
+      graph->set_error("operator refers to a missing operator code");
+      return false;
+    }
+    Vec in = op.vec(1, 4), out = op.vec(2, 4);
+    for (uint32_t k = 0; k < in.len; ++k)
+      if (!index_ok(in.at<int32_t>(k), true)) {
+        graph->set_error("operator " + std::to_string(i) + " input refers to a missing tensor");
+        return false;
+      }
+    for (uint32_t k = 0; k < out.len; ++k)
+      if (!index_ok(out.at<int32_t>(k), false)) {
+        graph->set_error("operator " + std::to_string(i) + " output refers to a missing tensor");
+        return false;
+      }
+  }
 
   // which tensors are constants of builtin ops (=> device copies)
   std::vector<char> builtin_const(tensors.len, 0);

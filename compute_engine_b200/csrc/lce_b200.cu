@@ -58,6 +58,19 @@ namespace {
   } while (0)
 
 inline cudaStream_t as_stream(void* s) { return static_cast<cudaStream_t>(s); }
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a PER-DEVICE attribute: one flag per (kernel
+// instantiation, device), so a process that drives several GPUs raises the limit on each of them.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  bool need() {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= 64) return true;
+    if (done[dev]) return false;
+    done[dev] = true;
+    return true;
+  }
+};
 // per-channel vectors (multiplier, bias, thresholds) are padded by one widest channel tile
 constexpr int kChanPad = 128;
 inline int cdiv(int a, int b) { return (a + b - 1) / b; }
@@ -157,13 +170,11 @@ size_t cta_smem_budget() {
 
 template <int V, int OUT>
 int launch_conv_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.need())
     CUDA_OK(cudaFuncSetAttribute(lce::bconv_kernel<V, OUT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(cta_smem_budget())));
-    attr_set = true;
-  }
   lce::bconv_kernel<V, OUT><<<grid, lce::kThreads, smem, s>>>(p);
   g_path[2].fetch_add(1, std::memory_order_relaxed);
   return launch_check("bconv_kernel");
@@ -175,13 +186,11 @@ size_t imma_smem_budget(int V) {
 
 template <int V, int OUT>
 int launch_imma_vo(const lce::ConvKParams& p, dim3 grid, size_t smem, cudaStream_t s) {
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce once;
+  if (once.need())
     CUDA_OK(cudaFuncSetAttribute(lce::bconv_imma_kernel<V, OUT>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(imma_smem_budget(V))));
-    attr_set = true;
-  }
   lce::bconv_imma_kernel<V, OUT><<<grid, lce::kIThreads, smem, s>>>(p);
   g_path[1].fetch_add(1, std::memory_order_relaxed);
   return launch_check("bconv_imma_kernel");
@@ -267,13 +276,13 @@ EncodeTiledFn tensor_map_encoder() {
   return fn;
 }
 int num_sms() {
-  static int n = [] {
-    int dev = 0, v = 148;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
-    return v;
-  }();
-  return n;
+  static int cache[64] = {};
+  int dev = 0, v = 148;
+  cudaGetDevice(&dev);
+  if (dev >= 0 && dev < 64 && cache[dev]) return cache[dev];
+  cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+  if (dev >= 0 && dev < 64) cache[dev] = v;
+  return v;
 }
 constexpr size_t kTcSmemBudget = 226u * 1024u;   // dynamic shared memory of the one CTA per SM
 
@@ -352,14 +361,10 @@ int tc_max_halo_px(const lce::ConvKParams& p) {
 template <int V, int OUT>
 int launch_tc_vo(const CUtensorMap& tm_in, const CUtensorMap& tm_res, const CUtensorMap& tm_out,
                  const lce::tc::TcParams& t, int grid, size_t smem, cudaStream_t s) {
-  static bool attr_set[64] = {};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64 || !attr_set[dev]) {  // the attribute is per device
+  static PerDeviceOnce once;
+  if (once.need())
     CUDA_OK(cudaFuncSetAttribute(lce::tc::bconv_tc_kernel<V, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  static_cast<int>(kTcSmemBudget)));
-    if (dev >= 0 && dev < 64) attr_set[dev] = true;
-  }
   lce::tc::bconv_tc_kernel<V, OUT><<<grid, lce::tc::kThreads, smem, s>>>(tm_in, tm_res, tm_out, t);
   g_path[0].fetch_add(1, std::memory_order_relaxed);
   return launch_check("bconv_tc_kernel");

@@ -1266,11 +1266,13 @@ static int conv2d_impl(const lce_f32_conv_desc* d, const float* in, const float*
     const long long threads = M * G;
     const size_t smem = direct_smem;
     if (smem > 48 * 1024) {
-      static bool attr = false;
-      if (!attr) {
+      static bool attr[64] = {};   // the attribute is per device
+      int dev = 0;
+      cudaGetDevice(&dev);
+      if (dev < 0 || dev >= 64 || !attr[dev]) {
         cudaFuncSetAttribute(conv_direct16_kernel<0, 0, 0, 4>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-        attr = true;
+        if (dev >= 0 && dev < 64) attr[dev] = true;
       }
     }
     // 128 threads = (128 / G) pixels x G groups, PX pixels each. PX trades shared-memory weight
@@ -1497,13 +1499,16 @@ int lce_b200_f32_stem_conv_dw_pw(const lce_f32_conv_desc* conv1, const lce_f32_c
   if (g1.B == 0 || g2.OH == 0 || g2.OW == 0) return 0;
   StemGeom s{g1.B, g1.H, g1.W, g1.Cin, g1.OH, g1.OW, g1.ph, g1.pw, g2.OH, g2.OW, g2.ph, g2.pw,
              g1.act, g2.act, g3.act};
-  static bool attr = false;
+  static bool attr_dev[64] = {};   // the attribute is per device
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const bool attr = dev >= 0 && dev < 64 && attr_dev[dev];
   const size_t smem = kStemSmemFloats * sizeof(float);
   if (!attr) {
     if (cudaFuncSetAttribute(stem_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(smem)) != cudaSuccess)
       return fail("stem_conv_dw_pw: cannot raise the shared-memory limit");
-    attr = true;
+    if (dev >= 0 && dev < 64) attr_dev[dev] = true;
   }
   dim3 grid((g2.OW + kStT - 1) / kStT, (g2.OH + kStT - 1) / kStT, g1.B);
   stem_fused_kernel<<<grid, 256, smem, as_stream(stream)>>>(in, w1, b1, w2, b2, w3, b3, out, s);

@@ -93,6 +93,19 @@ def bmaxpool_options(filter_hw, stride_hw, padding) -> bytes:
                          "filter_height": filter_hw[0]})
 
 
+def device_count() -> int:
+    return int(lib().lce_host_device_count())
+
+
+def set_device(index: int):
+    if lib().lce_host_set_device(int(index)) != 0:
+        raise HostError(f"cannot select CUDA device {index}")
+
+
+def get_device() -> int:
+    return int(lib().lce_host_get_device())
+
+
 def register_custom(name: str, registration_ptr: int):
     """Expose an external TfLiteRegistration* (e.g. the oracle test double) as `name`."""
     lib().lce_host_register_custom(name.encode(), C.c_void_p(registration_ptr))
@@ -210,13 +223,20 @@ class HostGraph:
         lib().lce_host_preserve_all_tensors(self._g, 1 if on else 0)
 
     @classmethod
-    def from_tflite(cls, model_bytes: bytes, device_arena=True):
+    def from_tflite(cls, model_bytes: bytes, device_arena=True, use_reference_bconv=False,
+                    use_indirect_bgemm=False):
+        """use_reference_bconv / use_indirect_bgemm: the selectors of RegisterLCECustomOps
+        (LCE/tflite/kernels/lce_ops_register.h:25-53): which registration "LceBconv2d" resolves
+        to -- its validation rules and, under zero padding, which of the reference's two results
+        is reproduced (include/lce_b200_types.h)."""
         L = lib()
-        L.lce_host_graph_from_tflite.restype = C.c_void_p
+        L.lce_host_graph_from_tflite_ex.restype = C.c_void_p
         err = C.c_char_p()
         buf = (C.c_uint8 * len(model_bytes)).from_buffer_copy(model_bytes)
-        h = L.lce_host_graph_from_tflite(buf, C.c_size_t(len(model_bytes)),
-                                         1 if device_arena else 0, C.byref(err))
+        h = L.lce_host_graph_from_tflite_ex(buf, C.c_size_t(len(model_bytes)),
+                                            1 if device_arena else 0,
+                                            1 if use_reference_bconv else 0,
+                                            1 if use_indirect_bgemm else 0, C.byref(err))
         if not h:
             raise HostError((err.value or b'').decode())
         g = cls.__new__(cls)

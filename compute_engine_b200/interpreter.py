@@ -6,11 +6,17 @@ the converter pins the batch to 1, LCE/mlir/transforms/set_batch_size.cc:9-22); 
 ``predict`` resizes the input tensors to the whole (mini-)batch, re-runs every op's
 ``prepare`` -- what TFLite's ResizeInputTensor + AllocateTensors does -- and runs the
 graph once per mini-batch on the device, replaying a captured CUDA graph.
+
+``devices=[...]`` shards every mini-batch over several GPUs of the box from ONE process: the
+model bytes are loaded onto each device once (constants are replicated; there is no transfer
+between devices afterwards), image i of a mini-batch goes to device i * D // n, all devices run
+concurrently on their own streams, and the outputs come back in input order. (bench.py's
+multi-GPU runs use one process per GPU instead, as the measurement contract asks.)
 """
 from __future__ import annotations
 
 import ctypes as C
-from typing import Iterator, List, Optional, Union
+from typing import Iterator, List, Optional, Sequence, Union
 
 import numpy as np
 
@@ -25,29 +31,47 @@ class Interpreter:
     def __init__(self, flatbuffer_model: bytes, num_threads: int = 1,
                  use_reference_bconv: bool = False, use_indirect_bgemm: bool = False,
                  use_xnnpack: bool = False, batch_size: Optional[int] = None,
-                 use_cuda_graph: bool = True, fuse: bool = True):
+                 use_cuda_graph: bool = True, fuse: bool = True,
+                 devices: Optional[Sequence[int]] = None):
         """flatbuffer_model: a serialized LCE model (`.tflite` bytes).
-        num_threads / use_xnnpack: accepted for interface parity; the device path has
-        no CPU threads to configure. use_reference_bconv / use_indirect_bgemm select
-        which of the reference's registrations' validation rules apply (all three run
-        the same CUDA kernel). batch_size: mini-batch used by predict (default: all).
-        fuse: apply the graph-level fusions (residual-block tail into LceBconv2d's epilogue,
-        max-pool + blur-pool); the outputs are bit-identical either way."""
+        num_threads / use_xnnpack: accepted for interface parity; the device path has no CPU
+        threads to configure. use_reference_bconv / use_indirect_bgemm: as in the reference
+        (interpreter.py:40-58 -> RegisterLCECustomOps), they choose the registration LceBconv2d
+        resolves to: Register_BCONV_2D_REF (the reference kernel's validation rules and, under
+        zero padding, its integer result) or Register_BCONV_2D_OPT_INDIRECT_BGEMM / the default
+        (the optimised kernels' rules and their float zero-padding correction).
+        batch_size: mini-batch used by predict (default: all). fuse: apply the graph-level fusions
+        (residual-block tail into LceBconv2d's epilogue, max-pool + blur-pool); the outputs are
+        bit-identical either way. devices: CUDA device indices to shard mini-batches over
+        (default: the current device only)."""
         if use_reference_bconv and use_indirect_bgemm:
             import warnings
             warnings.warn("'use_reference_bconv' and `use_indirect_bgemm` are both set to true. "
                           "use_indirect_bgemm==true will have no effect.")
+        self.devices = list(devices) if devices is not None else [None]
+        if not self.devices:
+            raise ValueError("devices must name at least one CUDA device")
+        self._graphs = []
+        self.fused_nodes_removed = 0
         try:
-            self._g = _host.HostGraph.from_tflite(bytes(flatbuffer_model), device_arena=True)
+            for d in self.devices:
+                with _on_device(d):
+                    g = _host.HostGraph.from_tflite(bytes(flatbuffer_model), device_arena=True,
+                                                    use_reference_bconv=use_reference_bconv,
+                                                    use_indirect_bgemm=use_indirect_bgemm)
+                    self._graphs.append(g)
+                    self.fused_nodes_removed = g.fuse_all() if fuse else 0
+                    g.allocate_tensors()
+                    if use_cuda_graph:
+                        g.enable_cuda_graph(True)
         except _host.HostError as e:
+            for g in self._graphs:
+                g.close()
             raise ValueError(f"Could not build the interpreter: {e}") from None
+        self._g = self._graphs[0]
         self.num_threads = num_threads
         self.batch_size = batch_size
-        self.fused_nodes_removed = self._g.fuse_all() if fuse else 0
-        self._g.allocate_tensors()
-        if use_cuda_graph:
-            self._g.enable_cuda_graph(True)
-        self._cur_batch = None
+        self._cur_batch = [None] * len(self._graphs)
 
     # ---- properties, as in interpreter_base.py:40-78 ----
     def _types(self, idx):
@@ -94,26 +118,41 @@ class Interpreter:
         return int(_host.lib().lce_host_tensor_zero_point(self._g._g, t)) if s != 0.0 else None
 
     # ---- execution ----
-    def _set_batch(self, n):
-        if n == self._cur_batch:
+    def _set_batch(self, gi, n):
+        if n == self._cur_batch[gi]:
             return
-        for t in self._g.inputs():
-            shape = list(self._g.shape(t))
+        g = self._graphs[gi]
+        for t in g.inputs():
+            shape = list(g.shape(t))
             shape[0] = n
-            self._g.resize_input(t, shape)
-        self._g.allocate_tensors()
-        self._cur_batch = n
+            g.resize_input(t, shape)
+        g.allocate_tensors()
+        self._cur_batch[gi] = n
 
     def _run(self, inputs: List[np.ndarray]) -> List[np.ndarray]:
         n = inputs[0].shape[0]
-        self._set_batch(n)
-        for t, a in zip(self._g.inputs(), inputs):
-            want = self._g.shape(t)
-            if tuple(a.shape) != tuple(want):
-                raise ValueError(f"input shape {a.shape} does not match {want}")
-            self._g.write(t, a)
-        self._g.invoke()
-        return [self._g.read(t) for t in self._g.outputs()]
+        D = len(self._graphs)
+        # image i -> device i * D // n: contiguous, ordered shards (compute_engine_b200.parallel.shard_range)
+        bounds = [(k * n) // D for k in range(D + 1)]
+        active = [k for k in range(D) if bounds[k + 1] > bounds[k]]
+        for k in active:                       # launch everywhere first: the devices overlap
+            lo, hi = bounds[k], bounds[k + 1]
+            with _on_device(self.devices[k]):
+                g = self._graphs[k]
+                self._set_batch(k, hi - lo)
+                for t, a in zip(g.inputs(), inputs):
+                    want = g.shape(t)
+                    part = a[lo:hi]
+                    if tuple(part.shape) != tuple(want):
+                        raise ValueError(f"input shape {part.shape} does not match {want}")
+                    g.write(t, part)
+                g.invoke()
+        parts = []
+        for k in active:                       # then gather in input order
+            with _on_device(self.devices[k]):
+                g = self._graphs[k]
+                parts.append([g.read(t) for t in g.outputs()])
+        return [np.concatenate(col) for col in zip(*parts)]
 
     def predict(self, x: Union[Data, Iterator[Data]], verbose: int = 0) -> Data:
         """Generates output predictions for the input samples (leading dim = samples)."""
@@ -147,4 +186,23 @@ class Interpreter:
         return self._g
 
     def close(self):
-        self._g.close()
+        for d, g in zip(self.devices, self._graphs):
+            with _on_device(d):
+                g.close()
+
+
+class _on_device:
+    """Make CUDA device `index` current for the duration of the block (None: leave it alone)."""
+
+    def __init__(self, index):
+        self.index, self.prev = index, None
+
+    def __enter__(self):
+        if self.index is not None:
+            self.prev = _host.get_device()
+            _host.set_device(self.index)
+
+    def __exit__(self, *exc):
+        if self.index is not None and self.prev is not None and self.prev >= 0:
+            _host.set_device(self.prev)
+        return False

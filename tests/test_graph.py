@@ -93,6 +93,60 @@ def test_unknown_custom_op_is_reported():
         H.HostGraph.from_tflite(b"garbage-bytes-here", device_arena=False)
 
 
+def test_malformed_tensor_indices_are_rejected():
+    """A .tflite whose operators or graph inputs / outputs point outside the tensor table is
+    refused by the reader (the op shells index context->tensors unchecked afterwards)."""
+    from compute_engine_b200.tflite_writer import TFLiteModel
+
+    def model(op_in, op_out, g_in, g_out):
+        m = TFLiteModel()
+        a = m.add_tensor("a", (1, 4, 4, 32))
+        b = m.add_tensor("b", (1, 4, 4, 1), np.int32)
+        m.add_op("LceQuantize", [a if op_in is None else op_in], [b if op_out is None else op_out],
+                 custom_options=b"")
+        m.inputs = [a if g_in is None else g_in]
+        m.outputs = [b if g_out is None else g_out]
+        return m.serialize()
+
+    H.HostGraph.from_tflite(model(None, None, None, None), device_arena=False).close()
+    for bad, what in ((model(7, None, None, None), "operator 0 input"),
+                      (model(-3, None, None, None), "operator 0 input"),
+                      (model(None, 2, None, None), "operator 0 output"),
+                      (model(None, -1, None, None), "operator 0 output"),
+                      (model(None, None, 5, None), "graph input"),
+                      (model(None, None, None, -1), "graph output")):
+        with pytest.raises(H.HostError, match=what + " refers to a missing tensor"):
+            H.HostGraph.from_tflite(bad, device_arena=False)
+
+
+def test_residual_fusion_skips_what_the_fused_kernel_cannot_do():
+    """A grouped LceBconv2d, or an ADD whose other operand only broadcasts onto the convolution's
+    output, stays unfused (the rewrite used to happen first and fail in Prepare)."""
+    from compute_engine_b200.tflite_writer import TFLiteModel, bconv2d_options
+    rng = np.random.default_rng(0)
+    for groups, res_shape in ((2, (1, 6, 6, 64)), (1, (64,))):
+        m = TFLiteModel()
+        x = m.add_tensor("x", (1, 6, 6, 128))
+        xq = m.add_tensor("xq", (1, 6, 6, 4), np.int32)
+        f = m.add_tensor("f", None, np.int32,
+                         data=rng.integers(-2**31, 2**31 - 1, (64, 3, 3, 4 // groups), dtype=np.int64).astype(np.int32))
+        mul = m.add_tensor("mul", None, np.float32, data=rng.uniform(0.1, 1, 64))
+        bias = m.add_tensor("bias", None, np.float32, data=rng.uniform(0.1, 1, 64))
+        y = m.add_tensor("y", (1, 6, 6, 64))
+        r = m.add_tensor("r", res_shape)
+        z = m.add_tensor("z", (1, 6, 6, 64))
+        m.add_op("LceQuantize", [x], [xq], custom_options=b"")
+        m.add_op("LceBconv2d", [xq, f, mul, bias, -1], [y], custom_options=bconv2d_options(128))
+        m.add_op("ADD", [y, r], [z])
+        m.inputs, m.outputs = [x, r], [z]
+        g = H.HostGraph.from_tflite(m.serialize(), device_arena=True)
+        assert g.fuse_residual_blocks() == 0 and g.num_nodes() == 3
+        g.close()
+        g = H.HostGraph.from_tflite(m.serialize(), device_arena=False)   # and it prepares unfused
+        g.allocate_tensors()
+        g.close()
+
+
 @pytest.mark.skipif(not os.path.isdir(TF_TESTDATA), reason="TFLite fixtures not on this box")
 def test_readers_on_tflite_own_fixtures():
     for name, n_ops in (("add.bin", 2), ("multi_add.bin", 3)):
@@ -235,6 +289,50 @@ def test_gpu_graph_parity_at_the_benched_shape(family):
     want_out, _ = R.run(m, [x[sel]])
     assert np.abs(fused[sel] - want_out[0]).max() <= 2e-4
     assert np.allclose(fused.sum(-1), 1.0, atol=1e-4)
+
+
+@pytest.mark.gpu
+def test_gpu_interpreter_selectors_and_devices():
+    """use_reference_bconv picks the reference kernel's zero-padding integers, the default the
+    optimised kernels' float correction (Bi-RealNet differs between them; QuickNet does not);
+    devices=[0, 0] shards every mini-batch over two graphs and returns the outputs in order."""
+    from compute_engine_b200.interpreter import Interpreter
+    blob = zoo.birealnet18(batch=1, image=64, seed=13)
+    x = np.random.default_rng(3).standard_normal((6, 64, 64, 3)).astype(np.float32)
+    m = R.parse(blob)
+    outs = {}
+    for name, kw, kind in (("default", {}, 1), ("ref", {"use_reference_bconv": True}, 0),
+                           ("indirect", {"use_indirect_bgemm": True}, 1)):
+        it = Interpreter(blob, **kw)
+        outs[name] = it.predict(x)
+        want, _ = R.run(m, [x], bconv_kind=kind)
+        assert np.abs(outs[name] - want[0]).max() < 2e-4, name
+        it.close()
+    assert np.array_equal(outs["default"], outs["indirect"])
+    assert not np.array_equal(outs["default"], outs["ref"])     # two different float computations
+    it2 = Interpreter(blob, devices=[0, 0], batch_size=5)
+    y2 = it2.predict(x)                                         # mini-batches 5 (3 + 2) and 1
+    it2.close()
+    assert np.array_equal(y2, outs["default"])
+
+
+@pytest.mark.gpu
+def test_gpu_benchmark_cli_flags():
+    """tools/lce_benchmark_model.py runs, and its --use_reference_bconv / --use_indirect_bgemm flags
+    reach the op resolver (lce_benchmark_tflite_model.cc:41-71)."""
+    import json as _json
+    import subprocess
+    import sys as _sys
+    tool = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools",
+                        "lce_benchmark_model.py")
+    for flags, reg in (([], "Register_BCONV_2D"),
+                       (["--use_reference_bconv=true"], "Register_BCONV_2D_REF"),
+                       (["--use_indirect_bgemm=true"], "Register_BCONV_2D_OPT_INDIRECT_BGEMM")):
+        out = subprocess.run([_sys.executable, tool, "--zoo=birealnet18", "--batch=2", "--num_runs=3",
+                              "--warmup_runs=2"] + flags, capture_output=True, text=True, timeout=600,
+                             check=True).stdout
+        d = _json.loads(out)
+        assert d["bconv_registration"] == reg and d["images_per_s"] > 0 and d["nodes"] > 0
 
 
 def test_residual_block_fusion_rewrites_the_graph():

@@ -295,3 +295,42 @@ def test_gpu_ops_under_a_host_arena_like_stock_tflite():
     want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias)
     assert np.array_equal(g.read(t_out).view(np.uint8), want.view(np.uint8))
     g.close()
+
+
+def test_registration_selectors_change_zero_padding_legality():
+    """HostGraph.from_tflite(use_reference_bconv / use_indirect_bgemm) resolves LceBconv2d like
+    RegisterLCECustomOps (lce_ops_register.h:25-53): the reference registration refuses zero
+    padding with an odd channel count, the optimised ones refuse it with a fused activation
+    (bconv2d.cc:188-200); the default accepts the union."""
+    from compute_engine_b200.tflite_writer import TFLiteModel, bconv2d_options
+
+    def model(cin, act):
+        rng = np.random.default_rng(0)
+        m = TFLiteModel()
+        cw = (cin + 31) // 32
+        xq = m.add_tensor("xq", (1, 6, 6, cw), np.int32)
+        f = m.add_tensor("f", None, np.int32,
+                         data=rng.integers(-2**31, 2**31 - 1, (8, 3, 3, cw), dtype=np.int64).astype(np.int32))
+        mul = m.add_tensor("mul", None, np.float32, data=rng.uniform(0.1, 1, 8))
+        bias = m.add_tensor("bias", None, np.float32, data=rng.uniform(0.1, 1, 8))
+        y = m.add_tensor("y", (1, 6, 6, 8))
+        m.add_op("LceBconv2d", [xq, f, mul, bias, -1], [y],
+                 custom_options=bconv2d_options(cin, pad_values=0, activation=act))
+        m.inputs, m.outputs = [xq], [y]
+        return m.serialize()
+
+    def prepares(blob, **kw):
+        g = H.HostGraph.from_tflite(blob, device_arena=False, **kw)
+        try:
+            g.allocate_tensors()
+            return True
+        except H.HostError as e:
+            assert "Zero-padding is only supported" in str(e)
+            return False
+        finally:
+            g.close()
+
+    odd, relu = model(33, 0), model(64, 1)
+    assert prepares(odd) and prepares(relu)                                  # default: union
+    assert not prepares(odd, use_reference_bconv=True) and prepares(relu, use_reference_bconv=True)
+    assert prepares(odd, use_indirect_bgemm=True) and not prepares(relu, use_indirect_bgemm=True)

@@ -46,7 +46,11 @@ def main():
     else:
         ap.error("--graph or --zoo is required")
     t0 = time.perf_counter()
-    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    # --use_reference_bconv / --use_indirect_bgemm pick the registration LceBconv2d resolves to,
+    # as lce_benchmark_tflite_model.cc:41-71 does through RegisterLCECustomOps; --num_threads is
+    # reported back but configures nothing (the device path has no CPU worker threads).
+    g = H.HostGraph.from_tflite(blob, device_arena=True, use_reference_bconv=a.use_reference_bconv,
+                                use_indirect_bgemm=a.use_indirect_bgemm)
     fused = g.fuse_all() if a.fuse else 0
     for t in g.inputs():
         shape = list(g.shape(t))
@@ -56,7 +60,10 @@ def main():
     init_ms = (time.perf_counter() - t0) * 1e3
     rng = np.random.default_rng(0)
     for t in g.inputs():                     # random inputs, like the reference's tool
-        g.write(t, rng.standard_normal(g.shape(t)).astype(g.dtype(t)))
+        if np.issubdtype(g.dtype(t), np.floating):
+            g.write(t, rng.standard_normal(g.shape(t)).astype(g.dtype(t)))
+        else:
+            g.write(t, rng.integers(-100, 100, g.shape(t)).astype(g.dtype(t)))
     g.enable_cuda_graph(a.use_cuda_graph and not a.enable_op_profiling)
     g.enable_profiling(a.enable_op_profiling)
     for _ in range(max(a.warmup_runs, 2)):
@@ -69,7 +76,10 @@ def main():
         g.invoke()
         g.synchronize()
         times.append((time.perf_counter() - t1) * 1e3)
+    registration = ("Register_BCONV_2D_REF" if a.use_reference_bconv else
+                    "Register_BCONV_2D_OPT_INDIRECT_BGEMM" if a.use_indirect_bgemm else "Register_BCONV_2D")
     out = {"graph": a.graph or f"zoo:{a.zoo}", "batch": a.batch, "nodes": g.num_nodes(),
+           "bconv_registration": registration, "num_threads": a.num_threads,
            "fused_nodes_removed": fused, "init_ms": round(init_ms, 2),
            "inference_ms": {"avg": round(float(np.mean(times)), 4),
                             "min": round(float(np.min(times)), 4),
