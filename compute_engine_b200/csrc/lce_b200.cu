@@ -418,19 +418,27 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   const size_t stage_bytes = static_cast<size_t>(c.tc_BN) * 32 * T::kWS;     // one ring slot
   const size_t resident_bytes = static_cast<size_t>(c.tc_BN) * 32 * t.taps * c.Cw_pg;  // all K words, dense
   const bool has_res = p.residual != nullptr;
-  int nS = tma_out ? (has_res ? T::kMaxNS : 2) : 0;
+  // Epilogue staging slots (16 KB = 128 rows x 32 channels each; with a shortcut they are also the
+  // TMA landing zone of the residual tiles, so their number is the prefetch depth of that stream):
+  // as many as fit beside the weights, an even number, at most 8 with and 4 without a shortcut.
+  const int ns_max = tma_out ? (has_res ? T::kMaxNS : 4) : 0;
+  const int ns_min = tma_out ? 2 : 0;
   const size_t fixed = T::kNR * raw_stage + T::kBarBytes + T::kTabBytes;
-  if (fixed + 2 * T::kSlotBytes + 3 * stage_bytes > kTcSmemBudget) return -1;
+  if (fixed + ns_min * T::kSlotBytes + 3 * stage_bytes > kTcSmemBudget) return -1;
   auto room = [&](int ns) { return kTcSmemBudget - fixed - static_cast<size_t>(ns) * T::kSlotBytes; };
-  const bool can_reside = c.tc_n_tiles == 1 && c.tc_S_t <= T::kMaxNB;
-  if (can_reside && room(nS) < resident_bytes && has_res && room(2) >= resident_bytes) nS = 2;
+  const bool can_reside = c.tc_n_tiles == 1 && c.tc_S_t <= T::kMaxNB && room(ns_min) >= resident_bytes;
+  int nS = ns_min;
   size_t b_bytes;
-  if (can_reside && room(nS) >= resident_bytes) {
+  if (can_reside) {
     t.b_resident = 1;
     t.nB = c.tc_S_t;
     b_bytes = (resident_bytes + 1023) & ~size_t{1023};
+    while (nS + 2 <= ns_max && room(nS + 2) >= b_bytes) nS += 2;
   } else {
     t.b_resident = 0;
+    // ring of weight stages (these layers are MMA / L2 bound, not shortcut bound): 4 slots when
+    // 3 stages still fit, the rest of the room goes to the ring (up to 6 stages)
+    while (nS + 2 <= std::min(ns_max, 4) && room(nS + 2) >= 3 * stage_bytes) nS += 2;
     const int nB = std::min<int>(static_cast<int>(room(nS) / stage_bytes), 6);
     if (nB < 3) return -1;
     t.nB = nB;

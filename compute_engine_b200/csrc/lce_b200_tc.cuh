@@ -51,7 +51,7 @@ constexpr int kWS = 8;            // K words per stage
 constexpr int kNA = 4;            // A stages in TMEM, 64 columns each
 constexpr int kNR = 2;            // activation-halo stages
 constexpr int kMaxNB = 32;        // weight stages in shared memory (barrier array size)
-constexpr int kMaxNS = 4;         // epilogue staging slots
+constexpr int kMaxNS = 8;         // epilogue staging slots (16 KB each)
 constexpr int kSlotBytes = kBM * 128;  // 128 rows x 32 columns x 4 B
 constexpr int kFirstExpWarp = 4, kNumExpWarps = 8, kFirstEpiWarp = 12, kNumEpiWarps = 8;
 constexpr int kTabBytes = 4 * 128 * 4 * 2;   // {mul, bias, wpop2, thr} x 128 channels, double-buffered
@@ -352,6 +352,63 @@ __global__ void wpop2_kernel(const int32_t* __restrict__ filter, int32_t* __rest
   int s = 0;
   for (int w = 0; w < Kw; ++w) s += __popc(static_cast<uint32_t>(f[w]));
   out[c] = 2 * s;
+}
+
+// OutputTransform<float> (output_transform.h:94-107) of one 32-channel chunk of one pixel, the fused
+// shortcut / activation of the ADD that followed, the chunk's sign bits, and the row written into the
+// (swizzled) staging buffer. Compile-time variants keep the common path free of branches so the
+// eight 4-channel groups schedule as independent chains.
+//   RES: a shortcut row is waiting in the buffer (in place); ACT: the ADD had a fused activation;
+//   ZPF: this pixel needs the optimised kernels' float zero-padding correction (edge pixels only).
+template <bool RES, bool ACT, bool ZPF>
+__device__ __forceinline__ uint32_t epilogue_float_chunk(const TcParams& p, const int (&x)[32], unsigned char* buf,
+                                                         int lane, const int* tab_cc, float act_lo, float act_hi,
+                                                         unsigned long long oob, int c0) {
+  uint32_t bits = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) {
+    float4* cell = reinterpret_cast<float4*>(buf + ((k ^ (lane & 7)) << 4));
+    const float4 mu = reinterpret_cast<const float4*>(tab_cc + 128)[k];
+    const float4 bi = reinterpret_cast<const float4*>(tab_cc + 256)[k];
+    float y0 = transform_float_x2(x[4 * k], p.clamp_min, p.clamp_max, mu.x, bi.x);
+    float y1 = transform_float_x2(x[4 * k + 1], p.clamp_min, p.clamp_max, mu.y, bi.y);
+    float y2 = transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z);
+    float y3 = transform_float_x2(x[4 * k + 3], p.clamp_min, p.clamp_max, mu.w, bi.w);
+    if (ZPF) {
+      // y += (-post_mul) * sum over the counted taps of (cin_pg - 2 popc(filter tap)): the float
+      // correction of zero_padding_correction.h:160-170,289-291 (mu is -post_mul)
+      int c0i = 0, c1i = 0, c2i = 0, c3i = 0;
+      for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
+        const int t = __ffsll(static_cast<long long>(mk)) - 1;
+        const int4 tv = __ldg(reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0) + k);
+        c0i += p.cin_pg - 2 * tv.x; c1i += p.cin_pg - 2 * tv.y;
+        c2i += p.cin_pg - 2 * tv.z; c3i += p.cin_pg - 2 * tv.w;
+      }
+      y0 = __fadd_rn(y0, __fmul_rn(mu.x, static_cast<float>(c0i)));
+      y1 = __fadd_rn(y1, __fmul_rn(mu.y, static_cast<float>(c1i)));
+      y2 = __fadd_rn(y2, __fmul_rn(mu.z, static_cast<float>(c2i)));
+      y3 = __fadd_rn(y3, __fmul_rn(mu.w, static_cast<float>(c3i)));
+    }
+    if (RES) {
+      const float4 rv = *cell;
+      y0 = __fadd_rn(y0, rv.x); y1 = __fadd_rn(y1, rv.y); y2 = __fadd_rn(y2, rv.z); y3 = __fadd_rn(y3, rv.w);
+      if (ACT) {
+        y0 = fminf(fmaxf(y0, act_lo), act_hi); y1 = fminf(fmaxf(y1, act_lo), act_hi);
+        y2 = fminf(fmaxf(y2, act_lo), act_hi); y3 = fminf(fmaxf(y3, act_lo), act_hi);
+      }
+    }
+    *cell = make_float4(y0, y1, y2, y3);
+    // LceQuantize of the value just written: bit = value < 0 (bitpack.h:159)
+    bits |= ((y0 < 0.0f ? 1u : 0u) | (y1 < 0.0f ? 2u : 0u) | (y2 < 0.0f ? 4u : 0u) | (y3 < 0.0f ? 8u : 0u)) << (4 * k);
+  }
+  return bits;
+}
+template <bool RES, bool ACT>
+__device__ __forceinline__ uint32_t epilogue_float_chunk_zp(const TcParams& p, const int (&x)[32], unsigned char* buf,
+                                                            int lane, const int* tab_cc, float act_lo, float act_hi,
+                                                            unsigned long long oob, int c0) {
+  if (oob != 0 && p.zp_float) return epilogue_float_chunk<RES, ACT, true>(p, x, buf, lane, tab_cc, act_lo, act_hi, oob, c0);
+  return epilogue_float_chunk<RES, ACT, false>(p, x, buf, lane, tab_cc, act_lo, act_hi, oob, c0);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -731,44 +788,17 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
           __syncwarp();
           if (res) mbar_wait_prof(&res_full[sl], (cntS / p.nS) & 1, 10, prof, pw[2]);
           uint32_t bits = 0;
+          if (OUT == LCE_OUT_RAW_ACC) {
 #pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            uint4* cell = reinterpret_cast<uint4*>(buf + ((k ^ (lane & 7)) << 4));
-            if (OUT == LCE_OUT_RAW_ACC) {
-              *cell = make_uint4(x[4 * k] >> 1, x[4 * k + 1] >> 1, x[4 * k + 2] >> 1, x[4 * k + 3] >> 1);
-            } else {
-              const float4 mu = reinterpret_cast<const float4*>(tab + 128 + cc * 32)[k];
-              const float4 bi = reinterpret_cast<const float4*>(tab + 256 + cc * 32)[k];
-              float y0 = transform_float_x2(x[4 * k], p.clamp_min, p.clamp_max, mu.x, bi.x);
-              float y1 = transform_float_x2(x[4 * k + 1], p.clamp_min, p.clamp_max, mu.y, bi.y);
-              float y2 = transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z);
-              float y3 = transform_float_x2(x[4 * k + 3], p.clamp_min, p.clamp_max, mu.w, bi.w);
-              if (oob != 0 && p.zp_float) {
-                // y += (-post_mul) * sum over the counted taps of (cin_pg - 2 popc(filter tap)): the
-                // float correction of zero_padding_correction.h:160-170,289-291 (mu is -post_mul)
-                int c0i = 0, c1i = 0, c2i = 0, c3i = 0;
-                for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
-                  const int t = __ffsll(static_cast<long long>(mk)) - 1;
-                  const int4 tv = __ldg(reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0) + k);
-                  c0i += p.cin_pg - 2 * tv.x; c1i += p.cin_pg - 2 * tv.y;
-                  c2i += p.cin_pg - 2 * tv.z; c3i += p.cin_pg - 2 * tv.w;
-                }
-                y0 = __fadd_rn(y0, __fmul_rn(mu.x, static_cast<float>(c0i)));
-                y1 = __fadd_rn(y1, __fmul_rn(mu.y, static_cast<float>(c1i)));
-                y2 = __fadd_rn(y2, __fmul_rn(mu.z, static_cast<float>(c2i)));
-                y3 = __fadd_rn(y3, __fmul_rn(mu.w, static_cast<float>(c3i)));
-              }
-              if (p.has_res) {
-                const float4 rv = *reinterpret_cast<const float4*>(cell);
-                y0 = __fadd_rn(y0, rv.x); y1 = __fadd_rn(y1, rv.y); y2 = __fadd_rn(y2, rv.z); y3 = __fadd_rn(y3, rv.w);
-                if (p.residual_act != LCE_ACT_NONE) {
-                  y0 = fminf(fmaxf(y0, act_lo), act_hi); y1 = fminf(fmaxf(y1, act_lo), act_hi);
-                  y2 = fminf(fmaxf(y2, act_lo), act_hi); y3 = fminf(fmaxf(y3, act_lo), act_hi);
-                }
-              }
-              *reinterpret_cast<float4*>(cell) = make_float4(y0, y1, y2, y3);
-              bits |= ((y0 < 0.0f ? 1u : 0u) | (y1 < 0.0f ? 2u : 0u) | (y2 < 0.0f ? 4u : 0u) | (y3 < 0.0f ? 8u : 0u)) << (4 * k);
-            }
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<uint4*>(buf + ((k ^ (lane & 7)) << 4)) =
+                  make_uint4(x[4 * k] >> 1, x[4 * k + 1] >> 1, x[4 * k + 2] >> 1, x[4 * k + 3] >> 1);
+          } else if (!res) {
+            bits = epilogue_float_chunk_zp<false, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, oob, c0);
+          } else if (p.residual_act == LCE_ACT_NONE) {
+            bits = epilogue_float_chunk_zp<true, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, oob, c0);
+          } else {
+            bits = epilogue_float_chunk_zp<true, true>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, oob, c0);
           }
           if (prof) pw[4] += clock64() - tc0;
           const long long tq0 = prof ? clock64() : 0;

@@ -204,6 +204,60 @@ __global__ void __launch_bounds__(128) probe_rate(int mode, int N, int iters, lo
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// ------------------------------------------------------------------ T5: issue interval vs accumulator
+// 16 MMAs unrolled per loop trip, descriptors precomputed (no scalar work between issues); ALT
+// accumulators taken in turn: if the ~100-cycle interval of T4 is the latency of the dependent
+// accumulate (same D back to back), it must shrink with ALT >= 2.
+template <int ALT>
+__global__ void __launch_bounds__(128) probe_rate2(int N, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01ff01ffu, 0, 0x02020202u);
+  fence_proxy_async();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  {
+    uint32_t v[8] = {0x01010101u, 0, 0x01000100u, 0, 1, 2, 3, 4};
+    for (int c = 0; c < 64; c += 8) tmem_st8(tb + 256 + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  long long t0 = 0;
+  if (warp == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_i8(128, N, 1, 1);
+    const uint32_t Bs = smem_u32(smem + 128 * 128);
+    const uint64_t bd0 = make_sdesc(Bs, 128, 1024, 0);
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    t0 = clock64();
+    if (pred) {
+      for (int it = 0; it < iters; it += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          mma_i8_ts(tb + (j % ALT) * N, tb + 256 + (j & 7) * 8, bd0 + (j & 3) * 16, idesc, 1);
+      }
+      tc_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------ T3: TMA
 __global__ void probe_tma1d(const __grid_constant__ CUtensorMap tm, int c0, int nbox, int32_t* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -447,6 +501,30 @@ int main() {
         printf("  alt=%d mode=%s N=%3d: %.3f ms, %.1f cycles/MMA (SM0), %.0f MAC/clk/SM, %.1f int8 TOP/s\n", alt, mode ? "TS" : "SS", N, ms,
                static_cast<double>(c[0]) / iters, 128.0 * N * 32.0 * iters / static_cast<double>(c[0]), 2.0 * macs / (ms * 1e-3) / 1e12);
       }
+    cudaFree(dc);
+  }
+  printf("T5: issue interval, unrolled x16, ALT accumulators in turn (TS mode)\n");
+  {
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * 8));
+    auto run = [&](auto kern, int alt, int N) {
+      CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      const int iters = 8192;
+      kern<<<148, 128, (128 + 256) * 128>>>(N, 64, dc);
+      CK(cudaDeviceSynchronize());
+      kern<<<148, 128, (128 + 256) * 128>>>(N, iters, dc);
+      CK(cudaDeviceSynchronize());
+      std::vector<long long> c(148);
+      CK(cudaMemcpy(c.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+      printf("  alt=%d N=%3d: %.1f cycles/MMA, %.0f MAC/clk/SM\n", alt, N, static_cast<double>(c[0]) / iters,
+             128.0 * N * 32.0 * iters / static_cast<double>(c[0]));
+    };
+    for (int N : {32, 64, 128}) {
+      run(probe_rate2<1>, 1, N);
+      run(probe_rate2<2>, 2, N);
+      if (N <= 64) run(probe_rate2<4>, 4, N);
+    }
+    run(probe_rate2<1>, 1, 256);
     cudaFree(dc);
   }
   printf("probe done\n");
