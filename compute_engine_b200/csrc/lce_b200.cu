@@ -147,6 +147,7 @@ struct GemmCore {
   uint8_t* tc_wt = nullptr;        // [n_tiles][S_t][BN x 128 B] int8 stage images
   int32_t* tc_wpop2 = nullptr;     // 2 * popcount of each filter row, padded
   int32_t* tc_tap_popc_t = nullptr;  // [taps][ldc], zero-padding correction
+  float* tc_zpc_cache = nullptr;     // [4][eff_h][eff_w][ldc], the optimised kernels' float corrections
   int tc_BN = 0, tc_n_tiles = 0, tc_CcB = 0, tc_n_chunks = 1, tc_flat = 0, tc_V = 1;
   int tc_S_full = 0, tc_S_last = 0, tc_S_t = 0, tc_ldc = 0;
   // shape-dependent part, cached per input shape
@@ -156,9 +157,9 @@ struct GemmCore {
   void release() {
     cudaFree(wt); cudaFree(mul); cudaFree(bias); cudaFree(thr); cudaFree(tap_popc);
     cudaFree(wt_nat); cudaFree(wpop);
-    cudaFree(tc_wt); cudaFree(tc_wpop2); cudaFree(tc_tap_popc_t);
+    cudaFree(tc_wt); cudaFree(tc_wpop2); cudaFree(tc_tap_popc_t); cudaFree(tc_zpc_cache);
     wt = wt_nat = wpop = nullptr; mul = bias = nullptr; thr = tap_popc = nullptr;
-    tc_wt = nullptr; tc_wpop2 = tc_tap_popc_t = nullptr; tc_ok = false;
+    tc_wt = nullptr; tc_wpop2 = tc_tap_popc_t = nullptr; tc_zpc_cache = nullptr; tc_ok = false;
   }
 };
 
@@ -457,6 +458,8 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   t.wt = c.tc_wt; t.mul = p.mul; t.bias = p.bias; t.wpop2 = c.tc_wpop2; t.thr = p.thr;
   t.tap_popc_t = p.tap_popc != nullptr ? c.tc_tap_popc_t : nullptr;
   t.zp_float = p.zp_float; t.cin_pg = p.cin_pg;
+  t.zpc_cache = c.tc_zpc_cache;
+  if (t.zp_float && t.zpc_cache == nullptr) return -1;
   t.out = p.out; t.packed_out = p.packed_out;
   t.fd_ohw = lce::make_fastdiv(static_cast<uint32_t>(ohw));
   t.fd_ow = lce::make_fastdiv(p.OW);
@@ -844,6 +847,21 @@ int lce_b200_bconv2d_create(const lce_bconv2d_desc* d, const int32_t* filter,
          to_device(fb.data(), padded * 4, padded * 4, &db);
     c.mul = static_cast<float*>(dm);
     c.bias = static_cast<float*>(db);
+    if (!rc && zero_pad && zp_opt_rule && c.tc_ok && c.tc_tap_popc_t != nullptr) {
+      // the optimised kernels' correction cache (zero_padding_correction.h:39-176), once per plan
+      const int eff_h = (d->filter_h - 1) * d->dilation_h + 1, eff_w = (d->filter_w - 1) * d->dilation_w + 1;
+      const size_t n = static_cast<size_t>(4) * eff_h * eff_w * c.tc_ldc;
+      if (cudaMalloc(&c.tc_zpc_cache, n * 4) != cudaSuccess || cudaMemset(c.tc_zpc_cache, 0, n * 4) != cudaSuccess) {
+        rc = fail("bconv2d: cannot allocate the zero-padding correction cache");
+      } else {
+        const int total = 4 * eff_h * eff_w * c.cout;
+        lce::tc::zpc_cache_kernel<<<cdiv(total, 256), 256>>>(c.tc_tap_popc_t, c.mul, c.tc_zpc_cache, c.cout, c.tc_ldc,
+                                                           d->filter_h, d->filter_w, d->dilation_h, d->dilation_w,
+                                                           d->channels_in / d->groups);
+        rc = launch_check("zpc_cache_kernel");
+        if (!rc && cudaDeviceSynchronize() != cudaSuccess) rc = fail("zpc_cache_kernel failed");
+      }
+    }
   } else if (!rc) {
     void* dt = nullptr;
     rc = to_device(thresholds, c.cout * 4, padded * 4, &dt);

@@ -81,6 +81,7 @@ struct TcParams {
   const int32_t* wpop2;    // 2 * popcount of each channel's filter row
   const int32_t* thr;
   const int32_t* tap_popc_t;  // [taps][ldc] or nullptr (zero-padding correction)
+  const float* zpc_cache;     // [4][eff_h][eff_w][ldc]: the optimised kernels' float corrections (zp_float)
   void* out;
   int32_t* packed_out;
   long long* prof;         // optional [16 warps][8] cycle counters of block 0 (LCE_B200_TC_PROF=1)
@@ -99,8 +100,10 @@ __device__ int g_tc_abort = 0;
 __device__ int g_tc_dbg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 __device__ __forceinline__ bool mbar_try(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
-  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
-               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  // the suspend-time hint (ns) lets a waiting warp sleep in hardware instead of spinning through
+  // the issue slots of the busy warps next to it; an arrival still wakes it at once
+  asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
   return ok != 0;
 }
 __device__ __noinline__ void tc_watchdog_fire(int tag, uint32_t parity, uint32_t cnt) {
@@ -248,46 +251,65 @@ __device__ __forceinline__ long long halo_word_base(const TcParams& p, long long
   return p.mode_flat ? ((px_lo * p.Cw) & ~3LL) : px_lo * p.CcB;
 }
 
-// Zero padding, which taps of output pixel (oy, ox) are corrected.
-//  reference kernel (zp_float == 0): the out-of-bounds taps (reference.h:100-103).
-//  optimised kernels (zp_float == 1): the taps that ApplyCorrection's case analysis counts
-//  (zero_padding_correction.h:39-176,232-285), restated literally -- for every image at least as
-//  large as the dilated filter that is again the set of out-of-bounds taps.
+// Zero padding with the reference kernel's integers (zp_float == 0): the out-of-bounds taps of
+// output pixel (oy, ox), each of which contributes cin_pg / 2 instead of popc(0 ^ w)
+// (reference.h:100-103).
 __device__ __forceinline__ unsigned long long zero_pad_tap_mask(const TcParams& p, int oy, int ox) {
   unsigned long long mask = 0;
-  if (!p.zp_float) {
-    const int iy0 = oy * p.sh - p.ph, ix0 = ox * p.sw - p.pw;
-    for (int fy = 0; fy < p.KH; ++fy)
-      for (int fx = 0; fx < p.KW; ++fx) {
-        const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
-        if (!(static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)))
-          mask |= 1ull << (fy * p.KW + fx);
-      }
-    return mask;
-  }
+  const int iy0 = oy * p.sh - p.ph, ix0 = ox * p.sw - p.pw;
+  for (int fy = 0; fy < p.KH; ++fy)
+    for (int fx = 0; fx < p.KW; ++fx) {
+      const int iy = iy0 + fy * p.dh, ix = ix0 + fx * p.dw;
+      if (!(static_cast<unsigned>(iy) < static_cast<unsigned>(p.H) && static_cast<unsigned>(ix) < static_cast<unsigned>(p.W)))
+        mask |= 1ull << (fy * p.KW + fx);
+    }
+  return mask;
+}
+// Zero padding as the optimised kernels do it (zp_float == 1): the row of the correction cache
+// that ApplyCorrection adds to output pixel (oy, ox), or -1 -- its case analysis restated
+// literally (zero_padding_correction.h:189-285), "cannot happen" fall-through included.
+__device__ __forceinline__ int zero_pad_cache_row(const TcParams& p, int oy, int ox) {
   const int eff_w = (p.KW - 1) * p.dw + 1, eff_h = (p.KH - 1) * p.dh + 1;
-  const int left_off = ((p.OW - 1) * p.sw + eff_w - p.W) / 2;   // zero_padding_correction.h:189-194
+  const int left_off = ((p.OW - 1) * p.sw + eff_w - p.W) / 2;
   const int top_off = ((p.OH - 1) * p.sh + eff_h - p.H) / 2;
   const int o_top = top_off - oy * p.sh, o_bot = -o_top - p.H + eff_h;
   const int o_left = left_off - ox * p.sw, o_right = -o_left - p.W + eff_w;
-  if (o_left <= 0 && o_right <= 0 && o_top <= 0 && o_bot <= 0) return 0;
+  if (o_left <= 0 && o_right <= 0 && o_top <= 0 && o_bot <= 0) return -1;
   int cs, X, Y;
   if (o_right <= 0 && o_top > 0 && o_bot < 0) { cs = 0; X = max(o_left, 0); Y = o_top; }
   else if (o_left < 0 && o_right > 0 && o_bot <= 0) { cs = 1; X = o_right; Y = max(o_top, 0); }
   else if (o_left > 0 && o_right < 0 && o_top <= 0) { cs = 2; X = o_left; Y = max(o_bot, 0); }
   else if (o_left <= 0 && o_top < 0 && o_bot > 0) { cs = 3; X = max(o_right, 0); Y = o_bot; }
-  else return 0;
-  for (int fy = 0; fy < p.KH; ++fy)
-    for (int fx = 0; fx < p.KW; ++fx) {
-      const int efx = p.dw * fx, efy = p.dh * fy;
+  else return -1;
+  if (X >= eff_w || Y >= eff_h) return -1;   // outside the cache: images smaller than the filter
+  return (cs * eff_h + Y) * eff_w + X;
+}
+// Plan time: CacheCorrectionValues (zero_padding_correction.h:39-176):
+// cache[case][y][x][c] = (-post_mul[c]) * sum over the taps the case counts of (cin_pg - 2 popc(tap)).
+// `mul` is the folded multiplier, which for float output IS -post_mul (bconv2d.cc:369-372).
+__global__ void zpc_cache_kernel(const int32_t* __restrict__ tap_popc_t, const float* __restrict__ mul,
+                                 float* __restrict__ cache, int cout, int ldc, int KH, int KW, int dh, int dw,
+                                 int cin_pg) {
+  const int eff_w = (KW - 1) * dw + 1, eff_h = (KH - 1) * dh + 1;
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * eff_h * eff_w * cout) return;
+  const int c = idx % cout;
+  int r = idx / cout;
+  const int x = r % eff_w;
+  r /= eff_w;
+  const int y = r % eff_h, cs = r / eff_h;
+  float corr = 0.0f;
+  for (int fy = 0; fy < KH; ++fy)
+    for (int fx = 0; fx < KW; ++fx) {
+      const int efx = dw * fx, efy = dh * fy;
       bool counted;
-      if (cs == 0) counted = efy < Y || efx < X;
-      else if (cs == 1) counted = efy < Y || (eff_w - efx) <= X;
-      else if (cs == 2) counted = (eff_h - efy) <= Y || efx < X;
-      else counted = (eff_h - efy) <= Y || (eff_w - efx) <= X;
-      if (counted) mask |= 1ull << (fy * p.KW + fx);
+      if (cs == 0) counted = efy < y || efx < x;
+      else if (cs == 1) counted = efy < y || (eff_w - efx) <= x;
+      else if (cs == 2) counted = (eff_h - efy) <= y || efx < x;
+      else counted = (eff_h - efy) <= y || (eff_w - efx) <= x;
+      if (counted) corr = __fadd_rn(corr, static_cast<float>(cin_pg - 2 * tap_popc_t[static_cast<size_t>(fy * KW + fx) * ldc + c]));
     }
-  return mask;
+  cache[static_cast<size_t>((cs * eff_h + y) * eff_w + x) * ldc + c] = __fmul_rn(mul[c], corr);
 }
 
 // bit 8i+s of w -> byte i of v[s], value 2^(s&3): 9 ALU instructions
@@ -359,11 +381,11 @@ __global__ void wpop2_kernel(const int32_t* __restrict__ filter, int32_t* __rest
 // (swizzled) staging buffer. Compile-time variants keep the common path free of branches so the
 // eight 4-channel groups schedule as independent chains.
 //   RES: a shortcut row is waiting in the buffer (in place); ACT: the ADD had a fused activation;
-//   ZPF: this pixel needs the optimised kernels' float zero-padding correction (edge pixels only).
+//   ZPF: some pixel of the warp needs the optimised kernels' float zero-padding correction.
 template <bool RES, bool ACT, bool ZPF>
 __device__ __forceinline__ uint32_t epilogue_float_chunk(const TcParams& p, const int (&x)[32], unsigned char* buf,
                                                          int lane, const int* tab_cc, float act_lo, float act_hi,
-                                                         unsigned long long oob, int c0) {
+                                                         int zrow, int c0) {
   uint32_t bits = 0;
 #pragma unroll
   for (int k = 0; k < 8; ++k) {
@@ -375,19 +397,12 @@ __device__ __forceinline__ uint32_t epilogue_float_chunk(const TcParams& p, cons
     float y2 = transform_float_x2(x[4 * k + 2], p.clamp_min, p.clamp_max, mu.z, bi.z);
     float y3 = transform_float_x2(x[4 * k + 3], p.clamp_min, p.clamp_max, mu.w, bi.w);
     if (ZPF) {
-      // y += (-post_mul) * sum over the counted taps of (cin_pg - 2 popc(filter tap)): the float
-      // correction of zero_padding_correction.h:160-170,289-291 (mu is -post_mul)
-      int c0i = 0, c1i = 0, c2i = 0, c3i = 0;
-      for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
-        const int t = __ffsll(static_cast<long long>(mk)) - 1;
-        const int4 tv = __ldg(reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0) + k);
-        c0i += p.cin_pg - 2 * tv.x; c1i += p.cin_pg - 2 * tv.y;
-        c2i += p.cin_pg - 2 * tv.z; c3i += p.cin_pg - 2 * tv.w;
+      // edge pixels: y += cache[row][c] (zero_padding_correction.h:289-291); lanes whose pixel
+      // needs no correction (zrow < 0) keep y untouched
+      const float4 cv = __ldg(reinterpret_cast<const float4*>(p.zpc_cache + static_cast<size_t>(max(zrow, 0)) * p.ldc + c0) + k);
+      if (zrow >= 0) {
+        y0 = __fadd_rn(y0, cv.x); y1 = __fadd_rn(y1, cv.y); y2 = __fadd_rn(y2, cv.z); y3 = __fadd_rn(y3, cv.w);
       }
-      y0 = __fadd_rn(y0, __fmul_rn(mu.x, static_cast<float>(c0i)));
-      y1 = __fadd_rn(y1, __fmul_rn(mu.y, static_cast<float>(c1i)));
-      y2 = __fadd_rn(y2, __fmul_rn(mu.z, static_cast<float>(c2i)));
-      y3 = __fadd_rn(y3, __fmul_rn(mu.w, static_cast<float>(c3i)));
     }
     if (RES) {
       const float4 rv = *cell;
@@ -406,9 +421,11 @@ __device__ __forceinline__ uint32_t epilogue_float_chunk(const TcParams& p, cons
 template <bool RES, bool ACT>
 __device__ __forceinline__ uint32_t epilogue_float_chunk_zp(const TcParams& p, const int (&x)[32], unsigned char* buf,
                                                             int lane, const int* tab_cc, float act_lo, float act_hi,
-                                                            unsigned long long oob, int c0) {
-  if (oob != 0 && p.zp_float) return epilogue_float_chunk<RES, ACT, true>(p, x, buf, lane, tab_cc, act_lo, act_hi, oob, c0);
-  return epilogue_float_chunk<RES, ACT, false>(p, x, buf, lane, tab_cc, act_lo, act_hi, oob, c0);
+                                                            int zrow, int c0) {
+  // warp-uniform choice: the correction variant only where some lane of the warp is an edge pixel
+  if (__any_sync(0xffffffffu, zrow >= 0))
+    return epilogue_float_chunk<RES, ACT, true>(p, x, buf, lane, tab_cc, act_lo, act_hi, zrow, c0);
+  return epilogue_float_chunk<RES, ACT, false>(p, x, buf, lane, tab_cc, act_lo, act_hi, zrow, c0);
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -717,11 +734,13 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
         named_bar_sync(1, kNumEpiWarps * 32);
       }
-      // zero padding: the taps of this pixel that need a correction
+      // zero padding: the reference kernel's out-of-bounds taps, or the optimised kernels' cache row
       unsigned long long oob = 0;
+      int zrow = -1;
       if (p.tap_popc_t != nullptr && row_ok) {
         const Pixel px = split_px(p, static_cast<uint32_t>(m));
-        oob = zero_pad_tap_mask(p, px.oy, px.ox);
+        if (p.zp_float) zrow = zero_pad_cache_row(p, px.oy, px.ox);
+        else oob = zero_pad_tap_mask(p, px.oy, px.ox);
       }
       mbar_wait_prof(&d_full[ds], (it >> 1) & 1, 9, prof, pw[1]);
       tc_fence_after();
@@ -753,7 +772,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
           x[4 * k + 2] = (static_cast<int>(accu[4 * k + 2]) >> 2) + wp.z;
           x[4 * k + 3] = (static_cast<int>(accu[4 * k + 3]) >> 2) + wp.w;
         }
-        if (oob != 0 && !p.zp_float) {
+        if (oob != 0) {
           for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
             const int t = __ffsll(static_cast<long long>(mk)) - 1;
             const int4* tp = reinterpret_cast<const int4*>(p.tap_popc_t + static_cast<size_t>(t) * p.ldc + c0);
@@ -794,11 +813,11 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
               *reinterpret_cast<uint4*>(buf + ((k ^ (lane & 7)) << 4)) =
                   make_uint4(x[4 * k] >> 1, x[4 * k + 1] >> 1, x[4 * k + 2] >> 1, x[4 * k + 3] >> 1);
           } else if (!res) {
-            bits = epilogue_float_chunk_zp<false, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, oob, c0);
+            bits = epilogue_float_chunk_zp<false, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
           } else if (p.residual_act == LCE_ACT_NONE) {
-            bits = epilogue_float_chunk_zp<true, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, oob, c0);
+            bits = epilogue_float_chunk_zp<true, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
           } else {
-            bits = epilogue_float_chunk_zp<true, true>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, oob, c0);
+            bits = epilogue_float_chunk_zp<true, true>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
           }
           if (prof) pw[4] += clock64() - tc0;
           const long long tq0 = prof ? clock64() : 0;

@@ -258,6 +258,75 @@ __global__ void __launch_bounds__(128) probe_rate2(int N, int iters, long long* 
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// ------------------------------------------------------------------ T6: per-stage overhead of the issuing thread
+// One "stage" = [optional: two try_waits on already-completed mbarriers] + fence + elect + 8 MMAs
+// with descriptors derived from loop-carried values (as the real kernel does) + [optional: two
+// tcgen05.commit]. Cycles per stage against the 8 * N / 2 the tensor pipe needs.
+__global__ void __launch_bounds__(128) probe_stage(int N, int stages, int do_wait, int do_commit, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar, done_bar[2], dummy[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01ff01ffu, 0, 0x02020202u);
+  fence_proxy_async();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&done_bar[0], 1); mbar_init(&done_bar[1], 1);
+    mbar_init(&dummy[0], 1); mbar_init(&dummy[1], 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  {
+    uint32_t v[8] = {0x01010101u, 0, 0x01000100u, 0, 1, 2, 3, 4};
+    for (int c = 0; c < 256; c += 8) tmem_st8(tb + 256 + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  long long t0 = 0;
+  if (warp == 0) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_i8(128, N, 1, 1);
+    const uint32_t Bs = smem_u32(smem + 128 * 128);
+    uint32_t as = 0;
+    t0 = clock64();
+    for (int st = 0; st < stages; ++st) {
+      if (do_wait) {               // parity 1 of a fresh barrier: complete at once
+        mbar_wait(&done_bar[0], 1);
+        mbar_wait(&done_bar[1], 1);
+      }
+      tc_fence_after();
+      const uint64_t bd0 = make_sdesc(Bs + (as & 1) * 2048, 128, 1024, 0);
+      const uint32_t a0 = tb + 256 + as * 64;
+      uint32_t pred;
+      asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+      if (pred) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) mma_i8_ts(tb, a0 + j * 8, bd0 + (j & 3) * 16, idesc, 1);
+        if (do_commit) {
+          tc_commit(&dummy[0]);
+          tc_commit(&dummy[1]);
+        }
+      }
+      __syncwarp();
+      if (++as == 4) as = 0;
+    }
+        uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    if (pred) tc_commit(&bar);
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------ T3: TMA
 __global__ void probe_tma1d(const __grid_constant__ CUtensorMap tm, int c0, int nbox, int32_t* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -525,6 +594,25 @@ int main() {
       if (N <= 64) run(probe_rate2<4>, 4, N);
     }
     run(probe_rate2<1>, 1, 256);
+    cudaFree(dc);
+  }
+  printf("T6: cycles per 8-MMA stage of the issuing thread (tensor time = 4 * N)\n");
+  {
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * 8));
+    CK(cudaFuncSetAttribute(probe_stage, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    for (int N : {64, 128})
+      for (int w = 0; w < 2; ++w)
+        for (int c = 0; c < 2; ++c) {
+          const int stages = 1024;
+          probe_stage<<<148, 128, (128 + 256) * 128>>>(N, 16, w, c, dc);
+          CK(cudaDeviceSynchronize());
+          probe_stage<<<148, 128, (128 + 256) * 128>>>(N, stages, w, c, dc);
+          CK(cudaDeviceSynchronize());
+          std::vector<long long> cy(148);
+          CK(cudaMemcpy(cy.data(), dc, 148 * 8, cudaMemcpyDeviceToHost));
+          printf("  N=%3d waits=%d commits=%d: %.0f cycles/stage (tensor %d)\n", N, w, c, static_cast<double>(cy[0]) / stages, 4 * N);
+        }
     cudaFree(dc);
   }
   printf("probe done\n");
