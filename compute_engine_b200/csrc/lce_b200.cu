@@ -305,7 +305,7 @@ int build_tc_weights(GemmCore* c, const int32_t* d_filter, bool want_tap_popc) {
   c->tc_n_tiles = cdiv(c->cout, c->tc_BN);
   if (Cw % 4 == 0) {
     c->tc_flat = 0; c->tc_V = 4;
-    c->tc_CcB = std::min(Cw, 64);
+    c->tc_CcB = std::min(Cw, 32);   // halo stage = pixels x 128 B at most
   } else {
     c->tc_flat = 1; c->tc_V = (Cw % 2 == 0) ? 2 : 1;
     c->tc_CcB = Cw;
@@ -425,7 +425,7 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   const int ns_max = tma_out ? (has_res ? T::kMaxNS : 4) : 0;
   const int ns_min = tma_out ? 2 : 0;
   const size_t fixed = T::kNR * raw_stage + T::kBarBytes + T::kTabBytes;
-  if (fixed + ns_min * T::kSlotBytes + 3 * stage_bytes > kTcSmemBudget) return -1;
+  if (fixed + ns_min * T::kSlotBytes > kTcSmemBudget) return -1;
   auto room = [&](int ns) { return kTcSmemBudget - fixed - static_cast<size_t>(ns) * T::kSlotBytes; };
   const bool can_reside = c.tc_n_tiles == 1 && c.tc_S_t <= T::kMaxNB && room(ns_min) >= resident_bytes;
   int nS = ns_min;
@@ -437,13 +437,11 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
     while (nS + 2 <= ns_max && room(nS + 2) >= b_bytes) nS += 2;
   } else {
     t.b_resident = 0;
-    // ring of weight stages (these layers are MMA / L2 bound, not shortcut bound): 4 slots when
-    // 3 stages still fit, the rest of the room goes to the ring (up to 6 stages)
-    while (nS + 2 <= std::min(ns_max, 4) && room(nS + 2) >= 3 * stage_bytes) nS += 2;
-    const int nB = std::min<int>(static_cast<int>(room(nS) / stage_bytes), 6);
-    if (nB < 3) return -1;
-    t.nB = nB;
-    b_bytes = nB * stage_bytes;
+    // the weights stream through a ring whose slots are the A stages' (one barrier pair per stage)
+    t.nB = T::kNA;
+    b_bytes = T::kNA * stage_bytes;
+    if (room(ns_min) < b_bytes) return -1;
+    while (nS + 2 <= std::min(ns_max, 4) && room(nS + 2) >= b_bytes) nS += 2;
   }
   t.nS = nS;
   t.Kw_total = t.taps * c.Cw_pg;
@@ -512,22 +510,22 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   static const bool prof_on = [] { const char* e = getenv("LCE_B200_TC_PROF"); return e && e[0] == '1'; }();
   if (prof_on) {
     // development aid: per-role cycle counters of block 0, printed after a synchronising copy
-    if (!d_prof) cudaMalloc(&d_prof, 16 * 8 * sizeof(long long));
-    cudaMemsetAsync(d_prof, 0, 16 * 8 * sizeof(long long), s);
+    if (!d_prof) cudaMalloc(&d_prof, 20 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 20 * 8 * sizeof(long long), s);
     t.prof = d_prof;
   }
   struct ProfDump {
     long long* d; cudaStream_t s; const T::TcParams* t; int grid;
     ~ProfDump() {
       if (!d) return;
-      long long h[128];
+      long long h[160];
       cudaStreamSynchronize(s);
       cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[tc prof] M=%lld BN=%d S_t=%d nB=%d res=%d resident=%d items=%d grid=%d\n", t->M, t->BN, t->S_t,
               t->nB, t->has_res, t->b_resident, t->n_tiles * t->m_tiles, grid);
-      const char* names[16] = {"act-prod", "mma", "w-prod", "res-prod", "exp0", "exp1", "exp2", "exp3", "exp4", "exp5", "exp6",
-                               "exp7", "epi0", "epi1", "epi2", "epi3"};
-      for (int w : {0, 1, 2, 3, 4, 8, 12})
+      const char* names[20] = {"exp0", "exp1", "exp2", "exp3", "exp4", "exp5", "exp6", "exp7", "epi0", "epi1", "epi2", "epi3",
+                               "epi4", "epi5", "epi6", "epi7", "act-prod", "res-prod", "w-prod", "mma"};
+      for (int w : {16, 19, 18, 17, 0, 4, 8, 12})
         fprintf(stderr, "[tc prof]  %-8s total=%lld  c1=%lld c2=%lld c3=%lld c4=%lld c5=%lld c6=%lld\n", names[w], h[w * 8],
                 h[w * 8 + 1], h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5], h[w * 8 + 6]);
     }

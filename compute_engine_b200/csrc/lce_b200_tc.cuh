@@ -10,24 +10,24 @@
 // the static weights.
 //
 // One persistent CTA per SM, 20 warps, warp-specialised:
-//   w0        activation producer  TMA (cp.async.bulk.tensor, SASS UTMALDG) of the packed HALO
+//   w16       activation producer  TMA (cp.async.bulk.tensor, SASS UTMALDG) of the packed HALO
 //                                  of a 128-pixel tile: the contiguous pixel range its taps touch,
 //                                  once per tile -- no im2col replication anywhere
-//   w1        MMA issuer           the warp runs converged so every descriptor lives in uniform
+//   w19       MMA issuer           the warp runs converged so every descriptor lives in uniform
 //                                  registers; one elected lane issues tcgen05.mma.cta_group::1
 //                                  .kind::i8, A from TMEM, B from shared memory, D (128 x BN int32)
 //                                  in TMEM, two D buffers
-//   w2        weight producer      cp.async.bulk of pre-expanded int8 stages (resident in shared
+//   w18       weight producer      cp.async.bulk of pre-expanded int8 stages (resident in shared
 //                                  memory for the whole kernel when they fit, else a ring)
-//   w3        shortcut producer    TMA tiles of the residual (fused ADD), SWIZZLE_128B
-//   w4..w11   expanders            thread = output pixel = TMEM lane: reads its taps' words from
+//   w17       shortcut producer    TMA tiles of the residual (fused ADD), SWIZZLE_128B
+//   w0..w7    expanders            thread = output pixel = TMEM lane: reads its taps' words from
 //                                  the halo (out-of-bounds taps read as 0 = "+1" padding,
 //                                  reference.h:106), expands bits -> bytes (9 ALU ops per word:
 //                                  bit 8i+s of a word becomes byte i of column s with VALUE
 //                                  2^(s&3); the weight byte there is +-(8 >> (s&3)), so every
 //                                  product is +-8 and D holds 8 * sum a*w') and writes them with
 //                                  tcgen05.st; two warps per TMEM lane quadrant take alternate stages
-//   w12..w19  epilogue             tcgen05.ld -> OutputTransform (output_transform.h:94-168,
+//   w8..w15   epilogue             tcgen05.ld -> OutputTransform (output_transform.h:94-168,
 //                                  unfused fmul + fadd) [+ shortcut, activation, next layer's sign
 //                                  bits] -> swizzled shared memory -> TMA store (UTMASTG); two warps
 //                                  per TMEM lane quadrant take alternate 32-channel chunks
@@ -53,7 +53,11 @@ constexpr int kNR = 2;            // activation-halo stages
 constexpr int kMaxNB = 32;        // weight stages in shared memory (barrier array size)
 constexpr int kMaxNS = 8;         // epilogue staging slots (16 KB each)
 constexpr int kSlotBytes = kBM * 128;  // 128 rows x 32 columns x 4 B
-constexpr int kFirstExpWarp = 4, kNumExpWarps = 8, kFirstEpiWarp = 12, kNumEpiWarps = 8;
+// Warp ids. The SM's schedulers favour the HIGHER warp id among eligible warps (measured: a
+// single-lane role at warp id 1 starved behind the busy expander / epilogue warps of its scheduler
+// and the tensor pipe idled half the time), so the latency-critical single-lane roles sit on top.
+constexpr int kFirstExpWarp = 0, kNumExpWarps = 8, kFirstEpiWarp = 8, kNumEpiWarps = 8;
+constexpr int kWarpActProd = 16, kWarpResProd = 17, kWarpWeightProd = 18, kWarpMma = 19;
 constexpr int kTabBytes = 4 * 128 * 4 * 2;   // {mul, bias, wpop2, thr} x 128 channels, double-buffered
 constexpr int kBarBytes = 1024;
 
@@ -454,12 +458,14 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
   if (tid == 0) {
     for (int i = 0; i < kMaxNB; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
     for (int i = 0; i < kNR; ++i) { mbar_init(&raw_full[i], 1); mbar_init(&raw_empty[i], kNumExpWarps); }
-    for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], 4); mbar_init(&a_empty[i], 1); }
+    // a stage is full when the four expander warps of its group have written the A columns and,
+    // when the weights stream through a ring (slot = A slot), the weight producer's copy has landed
+    for (int i = 0; i < kNA; ++i) { mbar_init(&a_full[i], p.b_resident ? 4 : 5); mbar_init(&a_empty[i], 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(&d_full[i], 1); mbar_init(&d_empty[i], kNumEpiWarps); }
     for (int i = 0; i < kMaxNS; ++i) { mbar_init(&res_full[i], 1); mbar_init(&res_empty[i], 4); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_base_p, 512);
+  if (warp == kWarpMma) tmem_alloc(tmem_base_p, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -474,7 +480,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
   long long pw[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   const long long prof_t0 = prof ? clock64() : 0;
 
-  if (warp == 0) {
+  if (warp == kWarpActProd) {
     // ===== activation producer =====
     if (lane == 0) {
       uint32_t cnt = 0;
@@ -504,13 +510,13 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kWarpMma) {
     // ===== MMA issuer: the whole warp runs the loop (values stay in uniform registers), one
     // elected lane issues =====
     const uint32_t idesc = make_idesc(p.BN);
     const uint32_t smem_base = smem_u32(smem);
     const uint32_t row32 = static_cast<uint32_t>(p.BN) * 32u;      // bytes of one K word of a stage image
-    uint32_t as = 0, a_par = 0, bs = 0, b_par = 0, it = 0;
+    uint32_t as = 0, a_par = 0, bs = 0, it = 0;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
       const uint32_t ds = it & 1;
       mbar_wait_prof(&d_empty[ds], ((it >> 1) & 1) ^ 1, 2, prof, pw[1]);
@@ -527,8 +533,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             b_addr = smem_base + wofs * row32;
             if (it == 0) mbar_wait_prof(&b_full[bs], 0, 3, prof, pw[2]);
           } else {
-            b_addr = smem_base + bs * (row32 * kWS);
-            mbar_wait_prof(&b_full[bs], b_par, 3, prof, pw[2]);
+            b_addr = smem_base + as * (row32 * kWS);   // ring: the weight slot IS the A slot
           }
           mbar_wait_prof(&a_full[as], a_par, 4, prof, pw[3]);
           tc_fence_after();
@@ -542,29 +547,24 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             } else {
               for (int j = 0; j < nw; ++j) mma_i8_ts2(d_addr, a_addr + j * 8, lo + j * 16, hi, idesc, j == 0 ? acc : 1u);
             }
-            tc_commit(&a_empty[as]);
-            if (!p.b_resident) tc_commit(&b_empty[bs]);
+            tc_commit(&a_empty[as]);   // frees the A columns and (ring) the weight slot
           }
           __syncwarp();
           acc = 1;
           wofs += nw;
           if (++as == kNA) { as = 0; a_par ^= 1; }
-          if (p.b_resident) {
-            ++bs;
-          } else if (++bs == static_cast<uint32_t>(p.nB)) {
-            bs = 0; b_par ^= 1;
-          }
+          ++bs;
         }
       }
-      if (p.b_resident) bs = 0;
+      bs = 0;
       if (elect_one()) tc_commit(&d_full[ds]);
       __syncwarp();
     }
-  } else if (warp == 2) {
+  } else if (warp == kWarpWeightProd) {
     // ===== weight producer =====
     if (lane == 0) {
       const uint32_t row32 = static_cast<uint32_t>(p.BN) * 32u;
-      uint32_t bs = 0, b_par = 0;
+      uint32_t bs = 0, as = 0, a_par = 0;
       for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int nt = static_cast<int>(fdiv(static_cast<uint32_t>(item), p.fd_mt));
         const uint8_t* src = p.wt + static_cast<size_t>(nt) * p.Kw_total * row32;
@@ -579,10 +579,11 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
               bulk_g2s(smem + wofs * row32, src + static_cast<size_t>(wofs) * row32, bytes, &b_full[bs]);
               ++bs;
             } else {
-              mbar_wait_prof(&b_empty[bs], b_par ^ 1, 5, prof, pw[1]);
-              mbar_arrive_expect_tx(&b_full[bs], bytes);
-              bulk_g2s(smem + bs * (row32 * kWS), src + static_cast<size_t>(wofs) * row32, bytes, &b_full[bs]);
-              if (++bs == static_cast<uint32_t>(p.nB)) { bs = 0; b_par ^= 1; }
+              // ring: slot `as` is shared with the A stage; its a_full barrier also counts this copy
+              mbar_wait_prof(&a_empty[as], a_par ^ 1, 5, prof, pw[1]);
+              mbar_arrive_expect_tx(&a_full[as], bytes);
+              bulk_g2s(smem + as * (row32 * kWS), src + static_cast<size_t>(wofs) * row32, bytes, &a_full[as]);
+              if (++as == kNA) { as = 0; a_par ^= 1; }
             }
             wofs += nw;
           }
@@ -590,7 +591,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         if (p.b_resident) break;   // loaded once, kept for every tile of this CTA
       }
     }
-  } else if (warp == 3) {
+  } else if (warp == kWarpResProd) {
     // ===== shortcut producer =====
     if (lane == 0 && p.has_res) {
       uint32_t cnt = 0;
@@ -607,7 +608,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         }
       }
     }
-  } else if (warp < kFirstEpiWarp) {
+  } else if (warp < kFirstExpWarp + kNumExpWarps) {
     // ===== expanders: thread = output pixel = TMEM lane =====
     const int q = warp & 3;
     const int group = (warp - kFirstExpWarp) >> 2;
@@ -884,7 +885,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
   __syncwarp();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == kWarpMma) tmem_dealloc(tmem, 512);
 }
 
 }  // namespace tc

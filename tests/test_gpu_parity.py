@@ -230,10 +230,24 @@ def test_bconv_host_buffer_call(capi):
 
 
 def test_bconv_refusals_match_reference(capi):
-    d = capi.BconvDesc(1, 8, 8, 33, 3, 3, 8, 1, 1, 1, 1, 1, capi.PADDING_SAME, 0, 0, 0, 1.0, 0)
+    # zero padding (bconv2d.cc:188-200): an odd channel count AND a fused activation satisfies
+    # neither the reference kernel's rule nor the optimised kernels'
+    d = capi.BconvDesc(1, 8, 8, 33, 3, 3, 8, 1, 1, 1, 1, 1, capi.PADDING_SAME, 0, 1, 0, 1.0, 0)
     with pytest.raises(capi.LceError, match="Zero-padding is only supported"):
         capi.BConv2d(d, np.zeros((8, 3, 3, 2), np.int32), np.ones(8, np.float32),
                      np.ones(8, np.float32))
+    # odd channel count, float output, no activation: only the optimised kernels' result exists
+    d = capi.BconvDesc(1, 8, 8, 33, 3, 3, 8, 1, 1, 1, 1, 1, capi.PADDING_SAME, 0, 0, 0, 1.0, 0)
+    plan = capi.BConv2d(d, np.zeros((8, 3, 3, 2), np.int32), np.ones(8, np.float32), np.ones(8, np.float32))
+    with pytest.raises(capi.LceError, match="Zero-padding is only supported"):
+        plan.set_zero_padding_mode(0)
+    plan.close()
+    # even channel count with a fused activation: only the reference kernel's result exists
+    d = capi.BconvDesc(1, 8, 8, 64, 3, 3, 8, 1, 1, 1, 1, 1, capi.PADDING_SAME, 0, 1, 0, 1.0, 0)
+    plan = capi.BConv2d(d, np.zeros((8, 3, 3, 2), np.int32), np.ones(8, np.float32), np.ones(8, np.float32))
+    with pytest.raises(capi.LceError, match="Zero-padding is only supported"):
+        plan.set_zero_padding_mode(1)
+    plan.close()
     d = capi.BconvDesc(1, 8, 8, 64, 3, 3, 8, 1, 1, 1, 1, 1, capi.PADDING_SAME, 3, 0, 0, 1.0, 0)
     with pytest.raises(capi.LceError, match="pad_values must be 0 or 1"):
         capi.BConv2d(d, np.zeros((8, 3, 3, 2), np.int32), np.ones(8, np.float32),

@@ -234,7 +234,10 @@ def test_gpu_single_op_models_through_registration(op):
         g.allocate_tensors()
         g.write(t_in, case.inp)
         g.invoke()
-        want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr)
+        # zero padding: the reference registration computes it in the integers, the optimised ones
+        # (and so the default CUDA registration) add the float correction afterwards
+        kind = 0 if op.endswith(":REF") else 1
+        want = L.bconv2d(case.desc, case.inp, case.filt, case.mul, case.bias, case.thr, kind=kind)
         got = g.read(t_out)
         assert got.shape == want.shape and np.array_equal(got.view(np.uint8), want.view(np.uint8)), s
         g.close()

@@ -12,9 +12,11 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <vector>
 
 #define CK(x)                                                                         \
@@ -327,6 +329,74 @@ __global__ void __launch_bounds__(128) probe_stage(int N, int stages, int do_wai
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+// ------------------------------------------------------------------ T7: kind::tf32 on TMA-loaded SWIZZLE_128B operands
+// D[128][N] = A[128][K] * B[N][K]^T in fp32 inputs (K-major rows of 32 floats = 128 B per swizzle
+// row), as the fp32 1x1 convolutions around the binary path would use it: does the tensor core
+// truncate or round fp32 -> tf32, and how accurate is the 3-pass hi/lo split?
+__device__ __forceinline__ void mma_tf32_ss(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n}\n" ::"r"(d), "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__global__ void __launch_bounds__(128) probe_tf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+                                                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+                                                  float* D, int N, int K, int passes) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar, lbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int nkb = K / 32;                       // 128-byte K blocks
+  unsigned char* As = smem;                     // [nkb][128 rows][128 B]
+  unsigned char* Al = As + nkb * 16384;
+  unsigned char* Bs = Al + nkb * 16384;         // [nkb][N rows][128 B]
+  unsigned char* Bl = Bs + nkb * N * 128;
+  if (tid == 0) {
+    mbar_init(&bar, 1); mbar_init(&lbar, 1);
+    fence_barrier_init();
+    mbar_expect_tx(&lbar, 2 * nkb * (16384 + N * 128));
+    for (int kb = 0; kb < nkb; ++kb) {
+      const CUtensorMap* maps[4] = {&tmA, &tmAlo, &tmB, &tmBlo};
+      unsigned char* dst[4] = {As + kb * 16384, Al + kb * 16384, Bs + kb * N * 128, Bl + kb * N * 128};
+      for (int q = 0; q < 4; ++q)
+        asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst[q])),
+                     "l"(reinterpret_cast<uint64_t>(maps[q])), "r"(smem_u32(&lbar)), "r"(kb * 32), "r"(0) : "memory");
+    }
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  mbar_wait(&lbar, 0);
+  if (tid == 0) {
+    tc_fence_after();
+    // c_format F32 (1), a/b format TF32 (2), K-major, N, M = 128
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (8u << 24);
+    uint32_t acc = 0;
+    for (int pass = 0; pass < passes; ++pass) {        // hi*hi, hi*lo, lo*hi
+      const unsigned char* a = pass == 2 ? Al : As;
+      const unsigned char* b = pass == 1 ? Bl : Bs;
+      for (int kb = 0; kb < nkb; ++kb)
+        for (int k8 = 0; k8 < 4; ++k8) {
+          const uint64_t ad = make_sdesc(smem_u32(a + kb * 16384) + k8 * 32, 16, 1024, 2);
+          const uint64_t bd = make_sdesc(smem_u32(b + kb * N * 128) + k8 * 32, 16, 1024, 2);
+          mma_tf32_ss(tb, ad, bd, idesc, acc);
+          acc = 1;
+        }
+    }
+    tc_commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t v[8];
+    tmem_ld8(tb + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
+    for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------ T3: TMA
 __global__ void probe_tma1d(const __grid_constant__ CUtensorMap tm, int c0, int nbox, int32_t* out) {
   extern __shared__ __align__(1024) unsigned char smem[];
@@ -614,6 +684,62 @@ int main() {
           printf("  N=%3d waits=%d commits=%d: %.0f cycles/stage (tensor %d)\n", N, w, c, static_cast<double>(cy[0]) / stages, 4 * N);
         }
     cudaFree(dc);
+  }
+  printf("T7: kind::tf32, TMA SWIZZLE_128B operands\n");
+  {
+    const int N = 128, K = 64;
+    std::vector<float> A(128 * K), B(N * K), Ah(128 * K), Al(128 * K), Bh(N * K), Bl(N * K);
+    srand(7);
+    auto rnd = [] { return (static_cast<float>(rand()) / RAND_MAX - 0.5f) * 4.0f; };
+    auto trunc_tf32 = [](float x) { uint32_t u; memcpy(&u, &x, 4); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+    auto rn_tf32 = [](float x) { uint32_t u; memcpy(&u, &x, 4); u += 0x00000FFFu + ((u >> 13) & 1u); u &= 0xFFFFE000u; float r; memcpy(&r, &u, 4); return r; };
+    for (size_t i = 0; i < A.size(); ++i) { A[i] = rnd(); Ah[i] = trunc_tf32(A[i]); Al[i] = A[i] - Ah[i]; }
+    for (size_t i = 0; i < B.size(); ++i) { B[i] = rnd(); Bh[i] = trunc_tf32(B[i]); Bl[i] = B[i] - Bh[i]; }
+    float *dA, *dAl, *dB, *dBl, *dAh, *dBh, *dD;
+    CK(cudaMalloc(&dA, A.size() * 4)); CK(cudaMalloc(&dAl, A.size() * 4)); CK(cudaMalloc(&dAh, A.size() * 4));
+    CK(cudaMalloc(&dB, B.size() * 4)); CK(cudaMalloc(&dBl, B.size() * 4)); CK(cudaMalloc(&dBh, B.size() * 4));
+    CK(cudaMalloc(&dD, 128 * N * 4));
+    CK(cudaMemcpy(dA, A.data(), A.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dAl, Al.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dAh, Ah.data(), A.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dB, B.data(), B.size() * 4, cudaMemcpyHostToDevice)); CK(cudaMemcpy(dBl, Bl.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dBh, Bh.data(), B.size() * 4, cudaMemcpyHostToDevice));
+    auto mk = [&](float* ptr, int rows) {
+      CUtensorMap tm;
+      cuuint64_t gdim[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(rows)};
+      cuuint64_t gstr[1] = {static_cast<cuuint64_t>(K) * 4};
+      cuuint32_t box[2] = {32, static_cast<cuuint32_t>(rows)};
+      cuuint32_t es[2] = {1, 1};
+      CUresult r = encode(&tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ptr, gdim, gstr, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) printf("  encode failed %d\n", static_cast<int>(r));
+      return tm;
+    };
+    CK(cudaFuncSetAttribute(probe_tf32, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    const size_t smem = 2 * (K / 32) * (16384 + N * 128);
+    std::vector<float> D(128 * N);
+    auto report = [&](const char* what) {
+      CK(cudaDeviceSynchronize());
+      CK(cudaMemcpy(D.data(), dD, D.size() * 4, cudaMemcpyDeviceToHost));
+      double e_full = 0, e_tr = 0, e_rn = 0, mag = 0;
+      for (int r = 0; r < 128; ++r)
+        for (int n = 0; n < N; ++n) {
+          double full = 0, tr = 0, rn = 0;
+          for (int k = 0; k < K; ++k) {
+            full += static_cast<double>(A[r * K + k]) * B[n * K + k];
+            tr += static_cast<double>(trunc_tf32(A[r * K + k])) * trunc_tf32(B[n * K + k]);
+            rn += static_cast<double>(rn_tf32(A[r * K + k])) * rn_tf32(B[n * K + k]);
+          }
+          const double d = D[r * N + n];
+          e_full = std::max(e_full, std::abs(d - full)); e_tr = std::max(e_tr, std::abs(d - tr)); e_rn = std::max(e_rn, std::abs(d - rn));
+          mag = std::max(mag, std::abs(full));
+        }
+      printf("  %s: max |D - exact| = %.3g, |D - truncated-inputs| = %.3g, |D - rounded-inputs| = %.3g (max |D| %.3g)\n", what, e_full,
+             e_tr, e_rn, mag);
+    };
+    probe_tf32<<<1, 128, smem>>>(mk(dA, 128), mk(dAl, 128), mk(dB, N), mk(dBl, N), dD, N, K, 1);
+    report("1 pass, raw fp32 operands   ");
+    probe_tf32<<<1, 128, smem>>>(mk(dAh, 128), mk(dAl, 128), mk(dBh, N), mk(dBl, N), dD, N, K, 3);
+    report("3 passes, hi/lo split        ");
   }
   printf("probe done\n");
   return 0;
