@@ -235,17 +235,37 @@ TfLiteStatus PoolDwInvoke(TfLiteContext* c, TfLiteNode* n) {
   return kTfLiteOk;
 }
 
-// ---- fused stem CONV_2D(3x3 s2 -> 16) + DEPTHWISE_CONV_2D(3x3 s2) + CONV_2D(1x1 -> 64) ---- //
-// Created by Graph::FuseFloatGlue; builtin_data = { conv1, depthwise, pointwise } BuiltinParams;
-// inputs [x, w1, b1, w2, b2, w3, b3].
+// ---- fused stem [DEQUANTIZE +] CONV_2D(3x3 s2, 3 -> 16) + DEPTHWISE_CONV_2D(3x3 s2) ---- //
+// Created by Graph::FuseStem; builtin_data = { conv1, depthwise } BuiltinParams;
+// inputs [x (float32, or the int8 / uint8 input of the removed DEQUANTIZE), w1, b1, w2, b2].
+struct StemBlob {
+  BuiltinParams c1, dw;
+};
 struct StemParams {
-  BuiltinParams c1, dw, pw;
+  BuiltinParams c1, dw;
+  // host copies of the (constant) filters and biases: the kernel takes them by value
+  std::vector<float> w1, b1, w2, b2;
 };
 void* StemInit(TfLiteContext*, const char* buffer, size_t length) {
   auto* p = new StemParams();
-  memset(p, 0, sizeof(*p));
-  if (buffer && length >= sizeof(StemParams)) memcpy(p, buffer, sizeof(StemParams));
+  memset(&p->c1, 0, sizeof(p->c1));
+  memset(&p->dw, 0, sizeof(p->dw));
+  if (buffer && length >= sizeof(StemBlob)) {
+    memcpy(&p->c1, buffer, sizeof(BuiltinParams));
+    memcpy(&p->dw, buffer + sizeof(BuiltinParams), sizeof(BuiltinParams));
+  }
   return p;
+}
+// Copy a constant float tensor to the host (device constants: one synchronous copy, at Prepare).
+bool HostCopy(const TfLiteTensor* t, std::vector<float>* out) {
+  out->clear();
+  if (!t) return true;   // optional bias
+  if (t->type != kTfLiteFloat32 || t->allocation_type != kTfLiteMmapRo || !t->data.raw) return false;
+  out->resize(t->bytes / sizeof(float));
+  if (OnDevice(t->data.raw))
+    return cudaMemcpy(out->data(), t->data.raw, out->size() * sizeof(float), cudaMemcpyDeviceToHost) == cudaSuccess;
+  memcpy(out->data(), t->data.raw, out->size() * sizeof(float));
+  return true;
 }
 void StemFree(TfLiteContext*, void* p) { delete static_cast<StemParams*>(p); }
 void FillConvDesc(lce_f32_conv_desc* d, const BuiltinParams& bp, int batch, int h, int w, int cin,
@@ -256,15 +276,12 @@ void FillConvDesc(lce_f32_conv_desc* d, const BuiltinParams& bp, int batch, int 
   d->dilation_h = bp.dilation_h; d->dilation_w = bp.dilation_w;
   d->padding = bp.padding; d->activation = bp.activation;
 }
-bool StemDescs(TfLiteContext* c, TfLiteNode* n, lce_f32_conv_desc* d1, lce_f32_conv_desc* d2,
-               lce_f32_conv_desc* d3) {
+bool StemDescs(TfLiteContext* c, TfLiteNode* n, lce_f32_conv_desc* d1, lce_f32_conv_desc* d2) {
   const auto& sp = *static_cast<StemParams*>(n->user_data);
   const TfLiteTensor* in = T(c, n->inputs, 0);
   const TfLiteTensor* w1 = T(c, n->inputs, 1);
   const TfLiteTensor* w2 = T(c, n->inputs, 3);
-  const TfLiteTensor* w3 = T(c, n->inputs, 5);
-  if (!in || !w1 || !w2 || !w3 || in->dims->size != 4 || w1->dims->size != 4 ||
-      w2->dims->size != 4 || w3->dims->size != 4)
+  if (!in || !w1 || !w2 || in->dims->size != 4 || w1->dims->size != 4 || w2->dims->size != 4)
     return false;
   int oh, ow;
   FillConvDesc(d1, sp.c1, in->dims->data[0], in->dims->data[1], in->dims->data[2],
@@ -273,27 +290,37 @@ bool StemDescs(TfLiteContext* c, TfLiteNode* n, lce_f32_conv_desc* d1, lce_f32_c
   if (lce_b200_f32_conv_out_shape(d1, &oh, &ow)) return false;
   FillConvDesc(d2, sp.dw, d1->batch, oh, ow, d1->out_c, w2);
   d2->out_c = w2->dims->data[3];
-  if (lce_b200_f32_conv_out_shape(d2, &oh, &ow)) return false;
-  FillConvDesc(d3, sp.pw, d1->batch, oh, ow, d2->out_c, w3);
-  d3->out_c = w3->dims->data[0];
   return true;
 }
 TfLiteStatus StemPrepare(TfLiteContext* c, TfLiteNode* n) {
-  lce_f32_conv_desc d1, d2, d3;
-  B_ENSURE(c, StemDescs(c, n, &d1, &d2, &d3), "fused stem: bad shapes");
+  lce_f32_conv_desc d1, d2;
+  B_ENSURE(c, StemDescs(c, n, &d1, &d2), "fused stem: bad shapes");
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  B_ENSURE(c, in->type == kTfLiteFloat32 || in->type == kTfLiteInt8 || in->type == kTfLiteUInt8,
+           "fused stem: the input must be float32, int8 or uint8");
+  B_ENSURE(c, d1.in_c == 3, "fused stem: three input channels expected");
+  auto& sp = *static_cast<StemParams*>(n->user_data);
+  if (sp.w1.empty()) {
+    B_ENSURE(c, HostCopy(T(c, n->inputs, 1), &sp.w1) && HostCopy(T(c, n->inputs, 2), &sp.b1) &&
+                    HostCopy(T(c, n->inputs, 3), &sp.w2) && HostCopy(T(c, n->inputs, 4), &sp.b2) &&
+                    sp.w1.size() == 16 * 27 && sp.w2.size() == 9 * 16 && (sp.b1.empty() || sp.b1.size() == 16) &&
+                    (sp.b2.empty() || sp.b2.size() == 16),
+             "fused stem: the filters and biases must be constant float tensors");
+  }
   int oh, ow;
-  B_CAPI(c, lce_b200_f32_conv_out_shape(&d3, &oh, &ow));
-  return Resize(c, T(c, n->outputs, 0), {d3.batch, oh, ow, d3.out_c});
+  B_CAPI(c, lce_b200_f32_conv_out_shape(&d2, &oh, &ow));
+  return Resize(c, T(c, n->outputs, 0), {d2.batch, oh, ow, d2.out_c});
 }
 TfLiteStatus StemInvoke(TfLiteContext* c, TfLiteNode* n) {
-  lce_f32_conv_desc d1, d2, d3;
-  StemDescs(c, n, &d1, &d2, &d3);
-  auto f = [&](int i) -> const float* {
-    const TfLiteTensor* t = T(c, n->inputs, i);
-    return t ? t->data.f : nullptr;
-  };
-  B_CAPI(c, lce_b200_f32_stem_conv_dw_pw(&d1, &d2, &d3, f(0), f(1), f(2), f(3), f(4), f(5), f(6),
-                                         T(c, n->outputs, 0)->data.f, lce_b200_get_stream()));
+  lce_f32_conv_desc d1, d2;
+  StemDescs(c, n, &d1, &d2);
+  const auto& sp = *static_cast<const StemParams*>(n->user_data);
+  const TfLiteTensor* in = T(c, n->inputs, 0);
+  const int in_type = in->type == kTfLiteFloat32 ? LCE_T_FLOAT : in->type == kTfLiteInt8 ? LCE_T_INT8 : LCE_T_BOOL;
+  B_CAPI(c, lce_b200_f32_stem_conv_dw(&d1, &d2, in_type, in->data.raw, in->params.scale, in->params.zero_point,
+                                      sp.w1.data(), sp.b1.empty() ? nullptr : sp.b1.data(), sp.w2.data(),
+                                      sp.b2.empty() ? nullptr : sp.b2.data(), T(c, n->outputs, 0)->data.f,
+                                      lce_b200_get_stream()));
   return kTfLiteOk;
 }
 

@@ -399,8 +399,9 @@ int Graph::FuseResidualBlocks() {
 const TfLiteRegistration* FusedPoolDepthwiseRegistration();  // builtin_ops.cc
 const TfLiteRegistration* FusedStemRegistration();
 
-// CONV_2D(3x3, stride 2, C_in <= 4 -> 16) -> DEPTHWISE_CONV_2D(3x3, stride 2, multiplier 1) ->
-// CONV_2D(1x1, stride 1, 16 -> 64), each intermediate consumed once: one node (QuickNet's stem).
+// [DEQUANTIZE ->] CONV_2D(3x3, stride 2, 3 -> 16) -> DEPTHWISE_CONV_2D(3x3, stride 2, multiplier 1),
+// each intermediate consumed once: one node (QuickNet's stem). The image is read once, as the
+// bytes the host shipped; the dequantised image and the first conv's map never reach HBM.
 int Graph::FuseStem() {
   auto sole_consumer = [&](int t, size_t after) -> size_t {
     if (std::find(outputs_.begin(), outputs_.end(), t) != outputs_.end()) return nodes_.size();
@@ -416,15 +417,25 @@ int Graph::FuseStem() {
     return reinterpret_cast<const BuiltinParams*>(r.builtin_blob.data());
   };
   auto dims4 = [&](int t, int d) { return tensors_[t].dims->size == 4 ? tensors_[t].dims->data[d] : -1; };
+  auto erase_node = [&](size_t victim) {
+    NodeRecord& v = *nodes_[victim];
+    LceB200IntArrayFree(v.node.inputs);
+    LceB200IntArrayFree(v.node.outputs);
+    LceB200IntArrayFree(v.node.temporaries);
+    LceB200IntArrayFree(v.node.intermediates);
+    nodes_.erase(nodes_.begin() + victim);
+  };
   for (size_t i = 0; i < nodes_.size(); ++i) {
     NodeRecord& c1 = *nodes_[i];
     if (c1.name != "builtin:3" || c1.initialized || c1.node.inputs->size < 3 ||
         c1.builtin_blob.size() < sizeof(BuiltinParams))
       continue;
     const int w1 = c1.node.inputs->data[1];
-    if (dims4(w1, 0) != 16 || dims4(w1, 1) != 3 || dims4(w1, 2) != 3 || dims4(w1, 3) > 4 ||
+    const int x = c1.node.inputs->data[0];
+    if (dims4(w1, 0) != 16 || dims4(w1, 1) != 3 || dims4(w1, 2) != 3 || dims4(w1, 3) != 3 ||
         bp(c1)->stride_h != 2 || bp(c1)->stride_w != 2 || bp(c1)->dilation_h != 1 ||
-        bp(c1)->dilation_w != 1 || tensors_[c1.node.outputs->data[0]].type != kTfLiteFloat32)
+        bp(c1)->dilation_w != 1 || tensors_[x].type != kTfLiteFloat32 ||
+        tensors_[c1.node.outputs->data[0]].type != kTfLiteFloat32)
       continue;
     const size_t di = sole_consumer(c1.node.outputs->data[0], i);
     if (di >= nodes_.size()) continue;
@@ -437,23 +448,29 @@ int Graph::FuseStem() {
         bp(dw)->stride_w != 2 || bp(dw)->dilation_h != 1 || bp(dw)->dilation_w != 1 ||
         bp(dw)->depth_multiplier != 1)
       continue;
-    const size_t pi = sole_consumer(dw.node.outputs->data[0], di);
-    if (pi >= nodes_.size()) continue;
-    NodeRecord& pw = *nodes_[pi];
-    if (pw.name != "builtin:3" || pw.initialized || pw.node.inputs->size < 3 ||
-        pw.builtin_blob.size() < sizeof(BuiltinParams))
-      continue;
-    const int w3 = pw.node.inputs->data[1];
-    if (dims4(w3, 0) != 64 || dims4(w3, 1) != 1 || dims4(w3, 2) != 1 || dims4(w3, 3) != 16 ||
-        bp(pw)->stride_h != 1 || bp(pw)->stride_w != 1)
-      continue;
-    std::vector<uint8_t> blob(3 * sizeof(BuiltinParams));
+    // the kernel takes the filters and biases by value: they must be constants
+    bool consts = true;
+    for (int t : {w1, c1.node.inputs->data[2], w2, dw.node.inputs->data[2]})
+      if (t >= 0 && tensors_[t].allocation_type != kTfLiteMmapRo) consts = false;
+    if (!consts) continue;
+    // a DEQUANTIZE that feeds only this conv is folded in: the kernel reads the quantised image
+    int src = x;
+    size_t qi = nodes_.size();
+    for (size_t k = 0; k < i; ++k) {
+      NodeRecord& dq = *nodes_[k];
+      if (dq.name == "builtin:6" && !dq.initialized && dq.node.outputs->size == 1 &&
+          dq.node.outputs->data[0] == x && dq.node.inputs->size == 1 && sole_consumer(x, k) == i &&
+          (tensors_[dq.node.inputs->data[0]].type == kTfLiteInt8 ||
+           tensors_[dq.node.inputs->data[0]].type == kTfLiteUInt8)) {
+        qi = k;
+        src = dq.node.inputs->data[0];
+      }
+    }
+    std::vector<uint8_t> blob(2 * sizeof(BuiltinParams));
     memcpy(blob.data(), bp(c1), sizeof(BuiltinParams));
     memcpy(blob.data() + sizeof(BuiltinParams), bp(dw), sizeof(BuiltinParams));
-    memcpy(blob.data() + 2 * sizeof(BuiltinParams), bp(pw), sizeof(BuiltinParams));
-    std::vector<int> ins{c1.node.inputs->data[0], w1, c1.node.inputs->data[2],
-                         w2, dw.node.inputs->data[2], w3, pw.node.inputs->data[2]};
-    std::vector<int> outs{pw.node.outputs->data[0]};
+    std::vector<int> ins{src, w1, c1.node.inputs->data[2], w2, dw.node.inputs->data[2]};
+    std::vector<int> outs{dw.node.outputs->data[0]};
     LceB200IntArrayFree(c1.node.inputs);
     LceB200IntArrayFree(c1.node.outputs);
     c1.node.inputs = MakeDims(ins);
@@ -461,17 +478,15 @@ int Graph::FuseStem() {
     c1.builtin_blob = blob;
     c1.node.builtin_data = c1.builtin_blob.data();
     c1.registration = FusedStemRegistration();
-    c1.name = "CONV_2D+DEPTHWISE_CONV_2D+CONV_2D";
-    for (size_t victim : {pi, di}) {   // erase the later node first
-      NodeRecord& v = *nodes_[victim];
-      LceB200IntArrayFree(v.node.inputs);
-      LceB200IntArrayFree(v.node.outputs);
-      LceB200IntArrayFree(v.node.temporaries);
-      LceB200IntArrayFree(v.node.intermediates);
-      nodes_.erase(nodes_.begin() + victim);
+    c1.name = qi < nodes_.size() ? "DEQUANTIZE+CONV_2D+DEPTHWISE_CONV_2D" : "CONV_2D+DEPTHWISE_CONV_2D";
+    erase_node(di);                         // the later node first
+    int removed = 1;
+    if (qi < nodes_.size()) {
+      erase_node(qi);
+      ++removed;
     }
     allocated_ = false;
-    return 2;
+    return removed;
   }
   return 0;
 }
@@ -511,14 +526,13 @@ int Graph::FuseConvQuantize() {
 
 int Graph::FuseFloatGlue() {
   if (!device_arena_) return 0;
-  // the one-pass stem is correct (bit-identical) but not yet faster than its three kernels
-  // (same instruction count, they are not memory bound): opt-in until it is
+  // LCE_B200_FUSE_STEM=0 / LCE_B200_FUSE_CONV_QUANT=0 switch the two fusions off (A/B runs)
   const char* stem_env = getenv("LCE_B200_FUSE_STEM");
-  int removed = (stem_env && stem_env[0] == '1') ? FuseStem() : 0;
-  // same verdict for CONV_2D -> LceQuantize: bit-identical, but the stand-alone pack kernel already
-  // streams at ~6 TB/s and the epilogue version saves nothing measurable (2.457 vs 2.436 ms/step)
+  int removed = (stem_env && stem_env[0] == '0') ? 0 : FuseStem();
+  // CONV_2D -> LceQuantize: the tensor-core pointwise kernel (lce_b200_pw.cuh) has the output row
+  // in registers and emits the sign words for free; other shapes pack with the stand-alone kernel
   const char* cq_env = getenv("LCE_B200_FUSE_CONV_QUANT");
-  if (cq_env && cq_env[0] == '1') removed += FuseConvQuantize();
+  if (!(cq_env && cq_env[0] == '0')) removed += FuseConvQuantize();
   for (size_t i = 0; i < nodes_.size(); ++i) {
     NodeRecord& pool = *nodes_[i];
     if (pool.name != "builtin:17" || pool.initialized ||

@@ -80,7 +80,7 @@ class Graph {
   // (QuickNet's anti-aliased down-sampling). Bit-identical. Returns the nodes removed.
   int FuseFloatGlue();
   int FuseConvQuantize();  // part of FuseFloatGlue: CONV_2D -> LceQuantize => conv with 2 outputs
-  int FuseStem();  // part of FuseFloatGlue: stem conv + depthwise + pointwise conv -> one node
+  int FuseStem();  // part of FuseFloatGlue: [DEQUANTIZE +] stem conv + depthwise conv -> one node
 
   // init (first time) + prepare of every node in order, then arena allocation.
   TfLiteStatus AllocateTensors();

@@ -20,6 +20,7 @@
 #include "lce_b200_kernels.cuh"
 #include "lce_b200_imma.cuh"
 #include "lce_b200_tc.cuh"
+#include "lce_b200_pw.cuh"
 
 namespace {
 thread_local std::string g_err;
@@ -536,6 +537,97 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
     default: return launch_tc_v<1>(c.out_type, tm_in, tm_res, tm_out, t, grid, smem, s);
   }
 }
+
+// fp32 pointwise convolution on the tensor cores (lce_b200_pw.cuh), called by the CONV_2D builtin
+// (lce_b200_builtins.cu). 0 = launched, -1 = shape not eligible (the caller's FMA kernels take
+// it), > 0 = error.
+std::atomic<uint64_t> g_pw_launches{0};
+}  // namespace
+namespace lce_b200_internal {
+int pw_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int32_t* packed, long long M, int N,
+                 int K, int act, void* stream) {
+  static const bool enabled = [] { const char* e = getenv("LCE_B200_PW_TF32"); return !(e && e[0] == '0'); }();
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enabled || enc == nullptr) return -1;
+  if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(filter) | reinterpret_cast<uintptr_t>(out) |
+       reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(packed)) & 15)
+    return -1;
+  const bool pairs = K == 16 && N == 64 && (M & 1) == 0;
+  if (!pairs && ((K & 31) != 0 || (N & 127) != 0 || K > 4096)) return -1;
+  namespace P = lce::pw;
+  P::PwParams p{};
+  p.M = pairs ? M / 2 : M;
+  p.N = pairs ? 128 : N;
+  p.KB = pairs ? 1 : K / 32;
+  p.n_tiles = p.N / 128;
+  const long long m_tiles = (p.M + 127) / 128;
+  if (m_tiles * p.n_tiles < 32 || m_tiles > (1 << 22)) return -1;   // a handful of tiles: the small-M GEMM
+  p.m_tiles = static_cast<int>(m_tiles);
+  p.act = act;
+  p.pairs = pairs ? 1 : 0;
+  p.w_resident = (p.n_tiles == 1 && p.KB <= P::kPwNS) ? 1 : 0;
+  p.bias_mask = pairs ? 63 : 0x7fffffff;
+  p.filter = filter;
+  p.bias = bias;
+  p.packed = packed;
+  const int Kp = pairs ? 32 : K;
+  CUtensorMap tm_a, tm_w, tm_out;
+  cuuint32_t es[2] = {1, 1};
+  cuuint32_t box_ld[2] = {32, 128}, box_st[2] = {32, 32};
+  {
+    cuuint64_t gd[2] = {static_cast<cuuint64_t>(Kp), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t gs[1] = {static_cast<cuuint64_t>(Kp) * 4};
+    if (enc(&tm_a, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(in), gd, gs, box_ld, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (pointwise input) failed");
+  }
+  tm_w = tm_a;
+  if (!pairs) {
+    cuuint64_t gd[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(N)};
+    cuuint64_t gs[1] = {static_cast<cuuint64_t>(K) * 4};
+    if (enc(&tm_w, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(filter), gd, gs, box_ld, es,
+            CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (pointwise filter) failed");
+  }
+  {
+    cuuint64_t gd[2] = {static_cast<cuuint64_t>(p.N), static_cast<cuuint64_t>(p.M)};
+    cuuint64_t gs[1] = {static_cast<cuuint64_t>(p.N) * 4};
+    if (enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, gd, gs, box_st, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+      return fail("cuTensorMapEncodeTiled (pointwise output) failed");
+  }
+  static PerDeviceOnce once;
+  if (once.need())
+    CUDA_OK(cudaFuncSetAttribute(P::pw_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P::kPwSmem)));
+  const int grid = static_cast<int>(std::min<long long>(m_tiles * p.n_tiles, num_sms()));
+  static long long* d_prof = nullptr;
+  static const bool prof_on = [] { const char* e = getenv("LCE_B200_TC_PROF"); return e && e[0] == '1'; }();
+  if (prof_on) {
+    if (!d_prof) cudaMalloc(&d_prof, 22 * 8 * sizeof(long long));
+    cudaMemsetAsync(d_prof, 0, 22 * 8 * sizeof(long long), static_cast<cudaStream_t>(stream));
+    p.prof = d_prof;
+  }
+  P::pw_tf32_kernel<<<grid, P::kPwThreads, P::kPwSmem, static_cast<cudaStream_t>(stream)>>>(tm_a, tm_w, tm_out, p);
+  if (prof_on) {
+    // development aid (LCE_TC_PROF build): per-role cycle counters of block 0
+    long long h[22 * 8];
+    cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    cudaMemcpy(h, d_prof, sizeof(h), cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[pw prof] M=%lld N=%d KB=%d resident=%d pairs=%d items=%lld grid=%d\n", p.M, p.N, p.KB, p.w_resident, p.pairs,
+            m_tiles * p.n_tiles, grid);
+    const char* names[22] = {"split0", "split1", "split2", "split3", "epi", "epi", "epi", "epi", "epi", "epi", "epi", "epi", "epi",
+                             "epi", "epi", "epi", "epi", "epi", "epi", "epi", "tma", "mma"};
+    for (int w : {20, 21, 0, 3, 4, 11, 19})
+      fprintf(stderr, "[pw prof]  %-7s w%-2d total=%lld  c1=%lld c2=%lld c3=%lld c4=%lld n=%lld\n", names[w], w, h[w * 8], h[w * 8 + 1],
+              h[w * 8 + 2], h[w * 8 + 3], h[w * 8 + 4], h[w * 8 + 5]);
+  }
+  g_pw_launches.fetch_add(1, std::memory_order_relaxed);
+  return launch_check("pw_tf32_kernel");
+}
+uint64_t pw_tf32_launches() { return g_pw_launches.load(); }
+}  // namespace lce_b200_internal
+namespace {
 
 // Build the tiled weights (+ optional tap popcounts) from an OHWI-packed filter
 // [cout][taps][Cw_pg] that may live on the host or the device.

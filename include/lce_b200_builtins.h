@@ -62,15 +62,18 @@ int lce_b200_f32_avg_pool(const lce_f32_pool_desc* d, const float* in_dev, float
 int lce_b200_f32_maxpool2x2_depthwise3x3(const lce_f32_pool_desc* pool, const lce_f32_conv_desc* dw,
                                          const float* in_dev, const float* filter_dev,
                                          const float* bias_dev, float* out_dev, void* stream);
-/* Fused stem CONV_2D(3x3, stride 2, C_in <= 4 -> 16) -> DEPTHWISE_CONV_2D(3x3, stride 2) ->
- * CONV_2D(1x1, 16 -> 64) (QuickNet's stem): one pass over the image, the two intermediate maps stay
- * in shared memory. `dw` / `pw` describe the ops on the previous op's output. Bit-identical to the
- * three kernels run one after the other. Biases may be NULL. */
-int lce_b200_f32_stem_conv_dw_pw(const lce_f32_conv_desc* conv1, const lce_f32_conv_desc* dw,
-                                 const lce_f32_conv_desc* pw, const float* in_dev,
-                                 const float* w1_dev, const float* b1_dev, const float* w2_dev,
-                                 const float* b2_dev, const float* w3_dev, const float* b3_dev,
-                                 float* out_dev, void* stream);
+/* Fused stem [DEQUANTIZE ->] CONV_2D(3x3, stride 2, 3 -> 16) -> DEPTHWISE_CONV_2D(3x3, stride 2)
+ * (QuickNet's stem): one pass over the image; the dequantised image and the first conv's map stay
+ * in shared memory. in_type LCE_T_FLOAT: `in_dev` is the float image (scale / zero point unused);
+ * LCE_T_INT8 / LCE_T_BOOL (= uint8): the quantised image, dequantised as float(scale * (q - zp))
+ * like lce_b200_dequantize_affine. `dw` describes the depthwise conv on the first conv's output.
+ * The filters and biases are HOST pointers (w1 OHWI [16][3][3][3], w2 [1][3][3][16]; biases may be
+ * NULL): 2.4 KB that travel by value in the kernel's parameter bank, where every FMA reads its
+ * weight as a constant operand. Bit-identical to the separate kernels run one after the other. */
+int lce_b200_f32_stem_conv_dw(const lce_f32_conv_desc* conv1, const lce_f32_conv_desc* dw, int in_type,
+                              const void* in_dev, double in_scale, int32_t in_zero_point,
+                              const float* w1_host, const float* b1_host, const float* w2_host,
+                              const float* b2_host, float* out_dev, void* stream);
 /* out[i] = act(a[i] (op) b[i % b_len]); b_len == n (same shape) or the last dim. */
 int lce_b200_f32_add(const float* a_dev, const float* b_dev, float* out_dev, int64_t n,
                      int64_t b_len, int activation, void* stream);

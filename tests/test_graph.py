@@ -349,47 +349,55 @@ def test_residual_block_fusion_rewrites_the_graph():
     assert names.count("LceQuantize") == 4             # first block of each stage
     assert "builtin:0" not in names and "LceBconv2d" not in names
     assert g.fuse_residual_blocks() == 0               # idempotent
-    # float glue: the three (max-pool 2x2 s1 -> blur depthwise 3x3 s2) pairs of the transitions
-    assert g.fuse_float_glue() == 3 and g.num_nodes() == 33
+    # float glue: the stem's conv 3x3 s2 -> depthwise 3x3 s2 pair (1 node removed), the four
+    # CONV_2D -> LceQuantize pairs (stem pointwise + three transitions) and the three
+    # (max-pool 2x2 s1 -> blur depthwise 3x3 s2) pairs of the transitions
+    assert g.fuse_float_glue() == 1 + 4 + 3 and g.num_nodes() == 28
     names = [g.node_name(i) for i in range(g.num_nodes())]
     assert names.count("MAX_POOL_2D+DEPTHWISE_CONV_2D") == 3 and "builtin:17" not in names
-    assert names.count("builtin:4") == 1               # the stem's depthwise stays
+    assert names[0] == "CONV_2D+DEPTHWISE_CONV_2D" and "builtin:4" not in names
+    assert names.count("CONV_2D+LceQuantize") == 4 and "LceQuantize" not in names
     assert g.fuse_float_glue() == 0                    # idempotent
     g.close()
 
 
-def test_opt_in_fusions(monkeypatch):
-    """LCE_B200_FUSE_STEM=1: conv 3x3 s2 -> depthwise 3x3 s2 -> conv 1x1 of the stem as one node;
-    LCE_B200_FUSE_CONV_QUANT=1: CONV_2D -> LceQuantize as a conv with a second, bitpacked output."""
-    monkeypatch.setenv("LCE_B200_FUSE_CONV_QUANT", "1")
-    g = H.HostGraph.from_tflite(zoo.quicknet(batch=1, image=64, seed=3), device_arena=True)
-    assert g.fuse_all() == 28 + 3 + 4 and g.num_nodes() == 29
+def test_fusion_switches_and_dequantize_folding(monkeypatch):
+    """An int8-input model: the DEQUANTIZE in front of the stem is folded into the fused stem node
+    (the kernel reads the quantised image). LCE_B200_FUSE_STEM=0 / LCE_B200_FUSE_CONV_QUANT=0
+    switch the two fusions off."""
+    blob = zoo.quicknet(batch=1, image=64, seed=3, input_type="int8")
+    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    assert g.num_nodes() == 65
+    assert g.fuse_all() == 28 + 2 + 4 + 3 and g.num_nodes() == 28
     names = [g.node_name(i) for i in range(g.num_nodes())]
-    assert names.count("CONV_2D+LceQuantize") == 4 and "LceQuantize" not in names
+    assert names[0] == "DEQUANTIZE+CONV_2D+DEPTHWISE_CONV_2D" and "builtin:6" not in names
     g.close()
-    monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")
-    g = H.HostGraph.from_tflite(zoo.quicknet(batch=1, image=64, seed=3), device_arena=True)
-    assert g.fuse_all() == 28 + 5 + 3 and g.num_nodes() == 28
+    monkeypatch.setenv("LCE_B200_FUSE_STEM", "0")
+    monkeypatch.setenv("LCE_B200_FUSE_CONV_QUANT", "0")
+    g = H.HostGraph.from_tflite(blob, device_arena=True)
+    assert g.fuse_all() == 28 + 3 and g.num_nodes() == 34
     names = [g.node_name(i) for i in range(g.num_nodes())]
-    assert names[0] == "CONV_2D+DEPTHWISE_CONV_2D+CONV_2D" and "builtin:4" not in names
-    assert names.count("CONV_2D+LceQuantize") == 3     # the transitions' 1x1 convs
-    assert names.count("LceQuantize") == 1             # after the fused stem
+    assert names[0] == "builtin:6" and names.count("builtin:4") == 1 and names.count("LceQuantize") == 4
     g.close()
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("family,image", [("quicknet", 64), ("quicknet", 88), ("birealnet18", 64)])
-def test_gpu_fused_graph_is_bit_identical_to_unfused(family, image, monkeypatch):
-    monkeypatch.setenv("LCE_B200_FUSE_STEM", "1")       # include the opt-in fusions
-    monkeypatch.setenv("LCE_B200_FUSE_CONV_QUANT", "1")
-    blob = zoo.MODELS[family](batch=1, image=image, seed=11)
-    x = np.random.default_rng(4).standard_normal((5, image, image, 3)).astype(np.float32)
+@pytest.mark.parametrize("family,image,input_type",
+                         [("quicknet", 64, "float32"), ("quicknet", 88, "float32"), ("quicknet", 64, "int8"),
+                          ("quicknet", 224, "int8"), ("quicknet", 100, "int8"), ("birealnet18", 64, "float32")])
+def test_gpu_fused_graph_is_bit_identical_to_unfused(family, image, input_type):
+    blob = zoo.MODELS[family](batch=1, image=image, seed=11, input_type=input_type)
+    if input_type == "int8":
+        x = np.random.default_rng(4).integers(-128, 128, (5, image, image, 3)).astype(np.int8)
+    else:
+        x = np.random.default_rng(4).standard_normal((5, image, image, 3)).astype(np.float32)
     outs = []
     for fuse in (False, True):
         g = H.HostGraph.from_tflite(blob, device_arena=True)
         if fuse:
             assert g.fuse_residual_blocks() > 0
-            assert g.fuse_float_glue() == (5 + 3 if family == "quicknet" else 0)
+            want = 0 if family != "quicknet" else (1 + 4 + 3 + (1 if input_type == "int8" else 0))
+            assert g.fuse_float_glue() == want
         g.resize_input(g.inputs()[0], x.shape)
         g.allocate_tensors()
         g.enable_cuda_graph(True)
