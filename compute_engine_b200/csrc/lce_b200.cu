@@ -626,6 +626,39 @@ int pw_tf32_conv(const float* in, const float* filter, const float* bias, float*
   return launch_check("pw_tf32_kernel");
 }
 uint64_t pw_tf32_launches() { return g_pw_launches.load(); }
+// CONV_2D 7x7 / stride 2 / 3 -> 64 (Bi-RealNet's stem) on tcgen05 kind::tf32 (lce_b200_pw.cuh):
+// 0 = launched, -1 = not this shape, > 0 = error.
+int stem7_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int B, int H, int W, int OH, int OW,
+                    int ph, int pw, int act, void* stream) {
+  static const bool enabled = [] { const char* e = getenv("LCE_B200_PW_TF32"); return !(e && e[0] == '0'); }();
+  EncodeTiledFn enc = tensor_map_encoder();
+  if (!enabled || enc == nullptr) return -1;
+  if ((reinterpret_cast<uintptr_t>(out) | reinterpret_cast<uintptr_t>(bias)) & 15) return -1;
+  namespace P = lce::pw;
+  P::Stem7Params p{};
+  p.M = static_cast<long long>(B) * OH * OW;
+  const long long m_tiles = (p.M + 127) / 128;
+  if (m_tiles < 32 || m_tiles > (1 << 23)) return -1;
+  p.H = H; p.W = W; p.OH = OH; p.OW = OW; p.ph = ph; p.pw = pw;
+  p.m_tiles = static_cast<int>(m_tiles);
+  p.act = act;
+  p.in = in; p.filter = filter; p.bias = bias;
+  CUtensorMap tm_out;
+  cuuint32_t es[2] = {1, 1};
+  cuuint32_t box_st[2] = {32, 32};
+  cuuint64_t gd[2] = {64, static_cast<cuuint64_t>(p.M)};
+  cuuint64_t gs[1] = {64 * 4};
+  if (enc(&tm_out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, out, gd, gs, box_st, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+          CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+    return fail("cuTensorMapEncodeTiled (7x7 stem output) failed");
+  static PerDeviceOnce once;
+  if (once.need())
+    CUDA_OK(cudaFuncSetAttribute(P::stem7_tf32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(P::kS7Smem)));
+  const int grid = static_cast<int>(std::min<long long>(m_tiles, num_sms()));
+  P::stem7_tf32_kernel<<<grid, P::kS7Threads, P::kS7Smem, static_cast<cudaStream_t>(stream)>>>(tm_out, p);
+  g_pw_launches.fetch_add(1, std::memory_order_relaxed);
+  return launch_check("stem7_tf32_kernel");
+}
 }  // namespace lce_b200_internal
 namespace {
 

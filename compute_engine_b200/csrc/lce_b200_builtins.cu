@@ -21,6 +21,9 @@ int launch_check(const char* what);   // lce_b200.cu
 // tcgen05 kind::tf32 pointwise convolution (lce_b200_pw.cuh): 0 launched, -1 not eligible
 int pw_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int32_t* packed, long long M, int N,
                  int K, int act, void* stream);
+// tcgen05 kind::tf32 7x7 / stride 2 / 3 -> 64 convolution (Bi-RealNet's stem): 0 launched, -1 not eligible
+int stem7_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int B, int H, int W, int OH, int OW,
+                    int ph, int pw, int act, void* stream);
 }  // namespace lce_b200_internal
 using lce_b200_internal::fail;
 using lce_b200_internal::launch_check;
@@ -1399,6 +1402,11 @@ static int conv2d_impl(const lce_f32_conv_desc* d, const float* in, const float*
       if (rc == 0 && pk) *packed_done = true;
       return rc;
     }
+  }
+  if (g.KH == 7 && g.KW == 7 && g.Cin == 3 && g.Cout == 64 && g.sh == 2 && g.sw == 2 && g.dh == 1 && g.dw == 1) {
+    const int rc = lce_b200_internal::stem7_tf32_conv(in, filter, bias, out, g.B, g.H, g.W, g.OH, g.OW, g.ph, g.pw, g.act,
+                                                      stream);
+    if (rc >= 0) return rc;
   }
   const int Gd = (g.Cout + 15) / 16;
   const size_t direct_smem =

@@ -321,6 +321,217 @@ pw_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
   if (wid == 20) tmem_dealloc(tmem_base, 512);
 }
 
+
+// ------------------------------------------------------------------ 7x7 / stride 2 stem on kind::tf32
+// Bi-RealNet's first layer, CONV_2D 7x7 stride 2, 3 -> 64 channels: K = 147 (five 32-float K
+// blocks, zero-padded), N = 64. As an FMA implicit GEMM it took 3.3 ms at batch 512, more than
+// all the binary layers together. Same 3-pass split as above; what differs is the A operand: no
+// im2col tensor exists, so no TMA -- thread = output pixel = TMEM lane gathers its own 147 input
+// values (21 contiguous floats per filter row; neighbours share them through L1), splits them and
+// writes hi | lo straight to TMEM. The filter (37 KB) is split into shared memory once per CTA.
+//   warps 0-7   gather + split: two warps per TMEM lane quarter take alternate K blocks
+//   warps 8-15  epilogue: (lane quarter, 32-column half)
+//   warp 16     MMA issuer (+ TMEM allocation)
+constexpr int kS7Threads = 544;
+constexpr int kS7K = 147, kS7KB = 5, kS7N = 64;
+constexpr int kS7WTile = 64 * 128;                 // 64 rows x 32 floats
+constexpr int kS7NS = 3, kS7NAcc = 4;
+constexpr size_t kS7Smem = kS7KB * 2 * kS7WTile + 8 * 4096 + 1024 + 1024;
+struct Stem7Params {
+  long long M;           // output pixels
+  int H, W, OH, OW, ph, pw;
+  int m_tiles, act;
+  const float* in;       // [B][H][W][3]
+  const float* filter;   // [64][7][7][3]
+  const float* bias;
+};
+constexpr uint32_t kIdescTf32N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
+
+template <int KBI>
+__device__ __forceinline__ void stem7_gather(const float* base, int row_pitch, uint32_t rowmask, int e_lo, int e_hi,
+                                             uint32_t (&h)[32], uint32_t (&l)[32]) {
+#pragma unroll
+  for (int j = 0; j < 32; ++j) {
+    const int k = KBI * 32 + j;
+    float x = 0.0f;
+    if (k < kS7K) {
+      const int fy = k / 21, e = k - fy * 21;     // compile-time after unrolling
+      if (((rowmask >> fy) & 1u) && e >= e_lo && e < e_hi) x = __ldg(base + fy * row_pitch + e);
+    }
+    const float hi = to_tf32(x);
+    h[j] = __float_as_uint(hi);
+    l[j] = __float_as_uint(to_tf32(x - hi));
+  }
+}
+
+__global__ void __launch_bounds__(kS7Threads, 1)
+stem7_tf32_kernel(const __grid_constant__ CUtensorMap tm_out, const Stem7Params p) {
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  unsigned char* w_st = smem;                               // [kS7KB][hi | lo][64 x 128 B]
+  unsigned char* epi = w_st + kS7KB * 2 * kS7WTile;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(epi + 8 * 4096);
+  uint64_t* ready = bars;                 // A stage written to TMEM   (128)
+  uint64_t* empty = bars + kS7NS;         // MMAs of the stage retired (commit)
+  uint64_t* acc_full = bars + 2 * kS7NS;
+  uint64_t* acc_empty = acc_full + kS7NAcc;
+  uint32_t* tmem_base_s = reinterpret_cast<uint32_t*>(acc_empty + kS7NAcc);
+
+  const int tid = threadIdx.x;
+  const int wid = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int lane = tid & 31;
+  if (tid == 0) {
+    for (int i = 0; i < kS7NS; ++i) {
+      mbar_init(&ready[i], 128);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < kS7NAcc; ++i) {
+      mbar_init(&acc_full[i], 1);
+      mbar_init(&acc_empty[i], 8);
+    }
+    fence_barrier_init();
+  }
+  if (wid == 16) tmem_alloc(tmem_base_s, 512);
+  // the filter, split hi | lo, in the K-major SWIZZLE_128B image the MMA reads (K padded with zeros)
+  for (int i = tid; i < kS7KB * 64 * 8; i += kS7Threads) {
+    const int c = i & 7, row = (i >> 3) & 63, kb = i >> 9;
+    float4 x;
+    float* xp = reinterpret_cast<float*>(&x);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = kb * 32 + c * 4 + q;
+      xp[q] = k < kS7K ? __ldg(p.filter + row * kS7K + k) : 0.0f;
+    }
+    float4 hh, ll;
+    split4(x, &hh, &ll);
+    float4* cell = reinterpret_cast<float4*>(w_st + kb * 2 * kS7WTile + row * 128 + ((c ^ (row & 7)) << 4));
+    *cell = hh;
+    *(cell + kS7WTile / 16) = ll;
+  }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_base_s;
+  constexpr uint32_t kACol = kS7NAcc * kS7N;   // A stages behind the accumulators
+
+  if (wid == 16) {
+    // ------------------------------------------------ MMA issuer
+    uint32_t cnt = 0, use = 0;
+    for (int it = blockIdx.x; it < p.m_tiles; it += gridDim.x, ++use) {
+      const int b = use % kS7NAcc;
+      mbar_wait_tc(&acc_empty[b], ((use / kS7NAcc) & 1) ^ 1, 2);
+      tc_fence_after();
+      const uint32_t d = tmem_base + b * kS7N;
+      for (int kb = 0; kb < kS7KB; ++kb, ++cnt) {
+        const int s = cnt % kS7NS;
+        mbar_wait_tc(&ready[s], (cnt / kS7NS) & 1, 3);
+        tc_fence_after();
+        const uint32_t a_hi = tmem_base + kACol + s * 64;
+        const uint32_t w_hi = sdesc_lo(smem_u32(w_st + kb * 2 * kS7WTile));
+        if (elect_one()) {
+#pragma unroll
+          for (int pass = 0; pass < 3; ++pass) {
+            const uint32_t a = a_hi + (pass == 0 ? 32 : 0);
+            const uint32_t w = w_hi + (pass == 1 ? (kS7WTile >> 4) : 0);
+#pragma unroll
+            for (int k8 = 0; k8 < 4; ++k8) mma_tf32_ts(d, a + 8 * k8, w + 2 * k8, kSdescHi, kIdescTf32N64, (kb | pass | k8) != 0);
+          }
+          tc_commit(&empty[s]);
+          if (kb == kS7KB - 1) tc_commit(&acc_full[b]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (wid < 8) {
+    // ------------------------------------------------ gather + split: warp (quarter, parity) takes every other K block
+    const int quarter = wid & 3, parity = wid >> 2;
+    const uint32_t a_t0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + kACol;
+    const int row_pitch = p.W * 3;
+    const long long ohw = static_cast<long long>(p.OH) * p.OW;
+    uint32_t cnt = 0;
+    for (int it = blockIdx.x; it < p.m_tiles; it += gridDim.x) {
+      const long long m = static_cast<long long>(it) * 128 + quarter * 32 + lane;
+      const long long mm = m < p.M ? m : p.M - 1;          // rows past the end gather a valid pixel; never stored
+      const int bi = static_cast<int>(mm / ohw);
+      const int rem = static_cast<int>(mm - bi * ohw);
+      const int oy = rem / p.OW, ox = rem - oy * p.OW;
+      const int iy0 = oy * 2 - p.ph, ix0 = ox * 2 - p.pw;
+      uint32_t rowmask = 0;
+#pragma unroll
+      for (int fy = 0; fy < 7; ++fy)
+        if (static_cast<unsigned>(iy0 + fy) < static_cast<unsigned>(p.H)) rowmask |= 1u << fy;
+      const int e_lo = 3 * max(0, -ix0), e_hi = 3 * min(7, p.W - ix0);
+      const float* base = p.in + ((static_cast<long long>(bi) * p.H + iy0) * p.W + ix0) * 3;
+      for (int kb = 0; kb < kS7KB; ++kb, ++cnt) {
+        if ((cnt & 1u) != static_cast<uint32_t>(parity)) continue;
+        const int s = cnt % kS7NS;
+        uint32_t h[32], l[32];
+        switch (kb) {
+          case 0: stem7_gather<0>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          case 1: stem7_gather<1>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          case 2: stem7_gather<2>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          case 3: stem7_gather<3>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          default: stem7_gather<4>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+        }
+        mbar_wait_tc(&empty[s], ((cnt / kS7NS) & 1) ^ 1, 6);   // the MMAs that last read this TMEM stage retired
+        tc_fence_after();
+        tmem_st32(a_t0 + s * 64, h);
+        tmem_st32(a_t0 + s * 64 + 32, l);
+        tmem_st_wait();
+        tc_fence_before();
+        mbar_arrive(&ready[s]);
+      }
+    }
+  } else {
+    // ------------------------------------------------ epilogue: warp -> (TMEM lane quarter q, 32-column half g)
+    const int q = wid & 3, g = (wid - 8) >> 2;
+    unsigned char* buf = epi + (wid - 8) * 4096;
+    uint32_t use = 0;
+    for (int it = blockIdx.x; it < p.m_tiles; it += gridDim.x, ++use) {
+      const int b = use % kS7NAcc;
+      mbar_wait_tc(&acc_full[b], (use / kS7NAcc) & 1, 5);
+      tc_fence_after();
+      uint32_t v[32];
+      tmem_ld32(tmem_base + (static_cast<uint32_t>(q * 32) << 16) + b * kS7N + g * 32, v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[b]);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + g * 32 + 4 * k));
+        float y0 = __fadd_rn(__uint_as_float(v[4 * k]), bi.x), y1 = __fadd_rn(__uint_as_float(v[4 * k + 1]), bi.y);
+        float y2 = __fadd_rn(__uint_as_float(v[4 * k + 2]), bi.z), y3 = __fadd_rn(__uint_as_float(v[4 * k + 3]), bi.w);
+        if (p.act == LCE_ACT_RELU) {
+          y0 = fmaxf(y0, 0.f); y1 = fmaxf(y1, 0.f); y2 = fmaxf(y2, 0.f); y3 = fmaxf(y3, 0.f);
+        } else if (p.act == LCE_ACT_RELU6) {
+          y0 = fminf(fmaxf(y0, 0.f), 6.f); y1 = fminf(fmaxf(y1, 0.f), 6.f);
+          y2 = fminf(fmaxf(y2, 0.f), 6.f); y3 = fminf(fmaxf(y3, 0.f), 6.f);
+        } else if (p.act == LCE_ACT_RELU_N1_TO_1) {
+          y0 = fminf(fmaxf(y0, -1.f), 1.f); y1 = fminf(fmaxf(y1, -1.f), 1.f);
+          y2 = fminf(fmaxf(y2, -1.f), 1.f); y3 = fminf(fmaxf(y3, -1.f), 1.f);
+        }
+        v[4 * k] = __float_as_uint(y0); v[4 * k + 1] = __float_as_uint(y1);
+        v[4 * k + 2] = __float_as_uint(y2); v[4 * k + 3] = __float_as_uint(y3);
+      }
+      if (lane == 0) tma_store_wait_read();   // the previous item's store has read this buffer
+      __syncwarp();
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        *reinterpret_cast<uint4*>(buf + lane * 128 + ((k ^ (lane & 7)) << 4)) =
+            make_uint4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tma_store_2d(&tm_out, buf, g * 32, it * 128 + q * 32);
+    }
+    if (lane == 0) tma_store_wait_all();
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (wid == 16) tmem_dealloc(tmem_base, 512);
+}
+
 }  // namespace pw
 }  // namespace lce
 

@@ -145,3 +145,41 @@ def test_tf32_pointwise_conv_matches_fp64_product(M, K, N, act, with_packed):
         words = (bits << torch.arange(32, device="cuda")).sum(-1)
         words = torch.where(words >= 2**31, words - 2**32, words).to(torch.int32)
         assert torch.equal(words, packed)
+
+
+@pytest.mark.parametrize("B,H,W,padding,act", [(8, 224, 224, PADDING_SAME, 0), (3, 101, 77, PADDING_SAME, 1),
+                                              (5, 64, 64, PADDING_VALID, 3)])
+def test_tf32_7x7_stem_matches_fp64_convolution(B, H, W, padding, act):
+    """CONV_2D 7x7 / stride 2 / 3 -> 64 (Bi-RealNet's stem; csrc/lce_b200_pw.cuh stem7_tf32_kernel:
+    per-thread im2col gather into TMEM, 3-pass tf32) against an fp64 convolution, same error bound
+    as the pointwise kernel: 2e-6 * sum|a||w|."""
+    torch, lib = _env()
+    import torch.nn.functional as F
+    g = torch.Generator(device="cpu").manual_seed(B * 7 + H)
+    x = (torch.randn(B, H, W, 3, generator=g) * 1.5).cuda()
+    w = (torch.randn(64, 7, 7, 3, generator=g) * 0.2).cuda()
+    b = torch.randn(64, generator=g).cuda()
+    d = ConvDesc(B, H, W, 3, 7, 7, 64, 2, 2, 1, 1, padding, act)
+    oh, ow = _out_hw(lib, d)
+    out = torch.full((B, oh, ow, 64), float("nan"), device="cuda")
+    assert lib.lce_b200_f32_conv2d(C.byref(d), _p(x), _p(w), _p(b), _p(out), None) == 0, lib.lce_b200_last_error().decode()
+    torch.cuda.synchronize()
+    if padding == PADDING_SAME:     # TFLite SAME: total = (o - 1) * s + k - in, before = total // 2
+        th, tw = max((oh - 1) * 2 + 7 - H, 0), max((ow - 1) * 2 + 7 - W, 0)
+        pad = (tw // 2, tw - tw // 2, th // 2, th - th // 2)
+    else:
+        pad = (0, 0, 0, 0)
+
+    def conv(xx, ww):
+        xp = F.pad(xx.permute(0, 3, 1, 2), pad)
+        return F.conv2d(xp, ww.permute(0, 3, 1, 2), stride=2).permute(0, 2, 3, 1)
+
+    ref = conv(x.double(), w.double()) + b.double()
+    mag = conv(x.abs().double(), w.abs().double()) + b.abs().double()
+    if act == 1:
+        ref = ref.clamp(min=0)
+    elif act == 3:
+        ref = ref.clamp(0, 6)
+    assert ref.shape == out.shape
+    rel = ((out.double() - ref).abs() / mag).max().item()
+    assert rel < 2e-6, rel
