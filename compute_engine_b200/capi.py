@@ -101,6 +101,13 @@ def _dev(t, dtype=None):
     return t.contiguous()
 
 
+def path_counts():
+    """Launches per binary inner product so far: [tcgen05, legacy mma.sync int8, XOR + POPC]."""
+    a = (C.c_uint64 * 3)()
+    lib().lce_b200_path_counts(a)
+    return [int(v) for v in a]
+
+
 def launch_count():
     return int(lib().lce_b200_launch_count())
 

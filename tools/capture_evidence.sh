@@ -21,8 +21,18 @@ python bench.py --workload bgemm_sweep --no-cpu-baseline > $O/bench_bgemm_sweep.
 # 3. ncu: launch list of the bench command, full capture of the binary convs of one step, aux kernels, glue
 timeout 600 $NCU --metrics gpu__time_duration.sum -c 600 --csv --log-file $O/ncu_launches.csv $BENCH --steps 2 --warmup 3 --no-e2e > $O/ncu_launches.log 2>&1
 timeout 900 $NCU --set full --import-source on -k regex:bconv_tc --launch-skip 48 -c 16 -o $O/ncu_bconv_tc -f $BENCH --steps 2 --warmup 3 --no-e2e > $O/ncu_bconv_tc.log 2>&1
-timeout 600 $NCU --set full -k "regex:pw_tf32|stem_conv_dw|pool2_dw3|gemm_small_m|mean_hw|softmax" --launch-skip 24 -c 12 -o $O/ncu_glue -f $BENCH --steps 2 --warmup 3 --no-e2e > $O/ncu_glue.log 2>&1
+timeout 600 $NCU --set full -k "regex:pw_tf32|stem_conv_dw|stem7_tf32|pool2_dw3|gemm_small_m|mean_hw|softmax" --launch-skip 24 -c 12 -o $O/ncu_glue -f $BENCH --steps 2 --warmup 3 --no-e2e > $O/ncu_glue.log 2>&1
 timeout 300 $NCU --set full -k "regex:bmaxpool_kernel|unpack_kernel|pack_generic_kernel|pack_f32_flat" --launch-skip 5 -c 5 -o $O/ncu_aux -f python tools/aux_kernels.py > $O/ncu_aux.log 2>&1
+# gpurun copies back at most 64 MiB: export what the summaries need here, keep only the binary-conv report
+for r in ncu_bconv_tc ncu_glue ncu_aux; do
+  ncu -i $O/$r.ncu-rep --page raw --csv > $O/${r}_raw.csv 2>/dev/null
+  ncu -i $O/$r.ncu-rep --page details --csv > $O/${r}_details.csv 2>/dev/null
+done
+ncu -i $O/ncu_bconv_tc.ncu-rep --page source --csv --print-source sass --launch-skip 0 --launch-count 1 > $O/ncu_bconv_tc_s1_sass.csv 2>/dev/null
+ncu -i $O/ncu_bconv_tc.ncu-rep --page source --csv --print-source sass --launch-skip 12 --launch-count 1 > $O/ncu_bconv_tc_s4_sass.csv 2>/dev/null
+rm -f $O/ncu_glue.ncu-rep $O/ncu_aux.ncu-rep $O/ncu_bconv_tc.ncu-rep
+timeout 300 $NCU --set full -k "regex:stem7_tf32" --launch-skip 2 -c 1 -o $O/ncu_stem7 -f python bench.py --workload birealnet18 --steps 1 --warmup 1 --no-cpu-baseline --no-extras --no-e2e > $O/ncu_stem7.log 2>&1
+ncu -i $O/ncu_stem7.ncu-rep --page raw --csv > $O/ncu_stem7_raw.csv 2>/dev/null; rm -f $O/ncu_stem7.ncu-rep
 # 4. memcheck of the new kernels
 timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_builtins.py -m gpu -q -x > $O/sanitizer_builtins.log 2>&1; tail -3 $O/sanitizer_builtins.log
 timeout 600 compute-sanitizer --tool memcheck python tools/tc_check.py conv fused > $O/sanitizer_tc.log 2>&1; tail -3 $O/sanitizer_tc.log

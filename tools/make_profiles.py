@@ -29,7 +29,10 @@ def ncu_summary(rep, dst):
     if not os.path.exists(path):
         print("missing", rep)
         return
-    raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if path.endswith(".csv"):      # exported on the GPU box (the reports are too large to travel)
+        raw = open(path).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", path, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[0]
     cols = [hdr.index(k) for k in KEEP if k in hdr]
@@ -77,9 +80,10 @@ def copy(src, dst):
 
 
 def main():
-    ncu_summary("ncu_bconv_tc.ncu-rep", f"{TAG}_ncu_bconv_tc_summary.csv")
-    ncu_summary("ncu_glue.ncu-rep", f"{TAG}_ncu_glue_summary.csv")
-    ncu_summary("ncu_aux.ncu-rep", f"{TAG}_ncu_aux_kernels_summary.csv")
+    ncu_summary("ncu_bconv_tc_raw.csv", f"{TAG}_ncu_bconv_tc_summary.csv")
+    ncu_summary("ncu_glue_raw.csv", f"{TAG}_ncu_glue_summary.csv")
+    ncu_summary("ncu_aux_raw.csv", f"{TAG}_ncu_aux_kernels_summary.csv")
+    ncu_summary("ncu_stem7_raw.csv", f"{TAG}_ncu_stem7_summary.csv")
     launch_list("ncu_launches.csv", f"{TAG}_ncu_launches_summary.csv")
     for src, dst in (("bench_default.json", f"{TAG}_bench_quicknet_b256_final.json"),
                      ("bench_reference.json", f"{TAG}_bench_reference_arm.json"),
