@@ -643,7 +643,6 @@ int stem7_tf32_conv(const float* in, const float* filter, const float* bias, flo
   p.m_tiles = static_cast<int>(m_tiles);
   p.act = act;
   p.in = in; p.filter = filter; p.bias = bias;
-  p.vec2 = ((W & 1) == 0 && (pw & 1) == 0 && (reinterpret_cast<uintptr_t>(in) & 7) == 0) ? 1 : 0;
   CUtensorMap tm_out;
   cuuint32_t es[2] = {1, 1};
   cuuint32_t box_st[2] = {32, 32};

@@ -327,13 +327,13 @@ pw_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 // blocks, zero-padded), N = 64. As an FMA implicit GEMM it took 3.3 ms at batch 512, more than
 // all the binary layers together. Same 3-pass split as above; what differs is the A operand: no
 // im2col tensor exists, so no TMA -- thread = output pixel = TMEM lane gathers its own 147 input
-// values (21 contiguous floats per filter row, read as float2; neighbours share them through L1), splits them and
+// values (21 contiguous floats per filter row; neighbours share them through L1), splits them and
 // writes hi | lo straight to TMEM. The filter (37 KB) is split into shared memory once per CTA.
 //   warps 0-7   gather + split: two warps per TMEM lane quarter take alternate K blocks
 //   warps 8-15  epilogue: (lane quarter, 32-column half)
 //   warp 16     MMA issuer (+ TMEM allocation)
 constexpr int kS7Threads = 544;
-constexpr int kS7K = 147, kS7Kp = 7 * 22, kS7KB = 5, kS7N = 64;   // K padded to 22 per filter row
+constexpr int kS7K = 147, kS7KB = 5, kS7N = 64;
 constexpr int kS7WTile = 64 * 128;                 // 64 rows x 32 floats
 constexpr int kS7NS = 3, kS7NAcc = 4;
 constexpr size_t kS7Smem = kS7KB * 2 * kS7WTile + 8 * 4096 + 1024 + 1024;
@@ -341,42 +341,26 @@ struct Stem7Params {
   long long M;           // output pixels
   int H, W, OH, OW, ph, pw;
   int m_tiles, act;
-  int vec2;              // every window starts 8-byte aligned: even W, even left padding, aligned base
   const float* in;       // [B][H][W][3]
   const float* filter;   // [64][7][7][3]
   const float* bias;
 };
 constexpr uint32_t kIdescTf32N64 = (1u << 4) | (2u << 7) | (2u << 10) | ((64u >> 3) << 17) | ((128u >> 4) << 24);
 
-// K is laid out as 7 filter rows of 22: 21 values (7 columns x 3 channels, contiguous in the NHWC
-// image) + one zero-weight pad, so that K pairs (k, k + 1), k even, never straddle a filter row or
-// a 32-wide K block and sit 8-byte aligned in the image when the window starts at an even column:
-// 10 LDG.64 + 1 LDG.32 per row instead of 21 LDG.32 (the gather is bound by L1 wavefronts).
 template <int KBI>
-__device__ __forceinline__ void stem7_gather(const float* base, int row_pitch, uint32_t rowmask, int e_lo, int e_hi, bool vec2,
+__device__ __forceinline__ void stem7_gather(const float* base, int row_pitch, uint32_t rowmask, int e_lo, int e_hi,
                                              uint32_t (&h)[32], uint32_t (&l)[32]) {
 #pragma unroll
-  for (int jj = 0; jj < 16; ++jj) {
-    const int k = KBI * 32 + 2 * jj;
-    float x0 = 0.0f, x1 = 0.0f;
-    if (k < kS7Kp) {
-      const int fy = k / 22, e = k - fy * 22;     // compile-time after unrolling; e is even
-      if ((rowmask >> fy) & 1u) {
-        const float* src = base + fy * row_pitch + e;
-        if (e < 20 && vec2 && e >= e_lo && e + 1 < e_hi) {
-          const float2 v = __ldg(reinterpret_cast<const float2*>(src));
-          x0 = v.x; x1 = v.y;
-        } else {
-          if (e >= e_lo && e < e_hi) x0 = __ldg(src);
-          if (e < 20 && e + 1 >= e_lo && e + 1 < e_hi) x1 = __ldg(src + 1);
-        }
-      }
+  for (int j = 0; j < 32; ++j) {
+    const int k = KBI * 32 + j;
+    float x = 0.0f;
+    if (k < kS7K) {
+      const int fy = k / 21, e = k - fy * 21;     // compile-time after unrolling
+      if (((rowmask >> fy) & 1u) && e >= e_lo && e < e_hi) x = __ldg(base + fy * row_pitch + e);
     }
-    const float h0 = to_tf32(x0), h1 = to_tf32(x1);
-    h[2 * jj] = __float_as_uint(h0);
-    h[2 * jj + 1] = __float_as_uint(h1);
-    l[2 * jj] = __float_as_uint(to_tf32(x0 - h0));
-    l[2 * jj + 1] = __float_as_uint(to_tf32(x1 - h1));
+    const float hi = to_tf32(x);
+    h[j] = __float_as_uint(hi);
+    l[j] = __float_as_uint(to_tf32(x - hi));
   }
 }
 
@@ -416,8 +400,7 @@ stem7_tf32_kernel(const __grid_constant__ CUtensorMap tm_out, const Stem7Params 
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int k = kb * 32 + c * 4 + q;
-      const int fy = k / 22, e = k - fy * 22;
-      xp[q] = (k < kS7Kp && e < 21) ? __ldg(p.filter + row * kS7K + fy * 21 + e) : 0.0f;
+      xp[q] = k < kS7K ? __ldg(p.filter + row * kS7K + k) : 0.0f;
     }
     float4 hh, ll;
     split4(x, &hh, &ll);
@@ -480,17 +463,16 @@ stem7_tf32_kernel(const __grid_constant__ CUtensorMap tm_out, const Stem7Params 
         if (static_cast<unsigned>(iy0 + fy) < static_cast<unsigned>(p.H)) rowmask |= 1u << fy;
       const int e_lo = 3 * max(0, -ix0), e_hi = 3 * min(7, p.W - ix0);
       const float* base = p.in + ((static_cast<long long>(bi) * p.H + iy0) * p.W + ix0) * 3;
-      const bool vec2 = p.vec2 != 0;
       for (int kb = 0; kb < kS7KB; ++kb, ++cnt) {
         if ((cnt & 1u) != static_cast<uint32_t>(parity)) continue;
         const int s = cnt % kS7NS;
         uint32_t h[32], l[32];
         switch (kb) {
-          case 0: stem7_gather<0>(base, row_pitch, rowmask, e_lo, e_hi, vec2, h, l); break;
-          case 1: stem7_gather<1>(base, row_pitch, rowmask, e_lo, e_hi, vec2, h, l); break;
-          case 2: stem7_gather<2>(base, row_pitch, rowmask, e_lo, e_hi, vec2, h, l); break;
-          case 3: stem7_gather<3>(base, row_pitch, rowmask, e_lo, e_hi, vec2, h, l); break;
-          default: stem7_gather<4>(base, row_pitch, rowmask, e_lo, e_hi, vec2, h, l); break;
+          case 0: stem7_gather<0>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          case 1: stem7_gather<1>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          case 2: stem7_gather<2>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          case 3: stem7_gather<3>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
+          default: stem7_gather<4>(base, row_pitch, rowmask, e_lo, e_hi, h, l); break;
         }
         mbar_wait_tc(&empty[s], ((cnt / kS7NS) & 1) ^ 1, 6);   // the MMAs that last read this TMEM stage retired
         tc_fence_after();
