@@ -122,6 +122,19 @@ def main():
                 name = subprocess.run(["c++filt", k], capture_output=True, text=True).stdout.strip()[:160]
                 f.write(f"{name}\n    {json.dumps(c, sort_keys=True)}\n")
     print("wrote sass mnemonics")
+    # and the instructions themselves for the three tcgen05 kernels
+    want = ("bconv_tc_kernelILi4ELi0", "pw_tf32_kernel", "stem7_tf32_kernel")
+    with open(os.path.join(OUT, f"{TAG}_sass_tcgen05_excerpt.txt"), "w") as f:
+        f.write("cuobjdump -sass compute_engine_b200/liblce_b200.so, lines with tcgen05 / TMA / TMEM instructions\n")
+        cur = None
+        for ln in sass.splitlines():
+            if "Function :" in ln:
+                cur = ln.split("Function :")[1].strip()
+                if any(w in cur for w in want):
+                    f.write("\n== " + cur + "\n")
+            elif cur and any(w in cur for w in want) and any(t in ln for t in ("UTCIMMA", "UTCHMMA", "UTCBAR", "UTCATOMSWS", "LDTM", "STTM", "UTMALDG", "UTMASTG", "UBLKCP", "UTMACMDFLUSH")):
+                f.write(ln.rstrip()[:140] + "\n")
+    print("wrote sass excerpt")
 
 
 if __name__ == "__main__":
