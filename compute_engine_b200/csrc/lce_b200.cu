@@ -545,23 +545,27 @@ std::atomic<uint64_t> g_pw_launches{0};
 }  // namespace
 namespace lce_b200_internal {
 int pw_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int32_t* packed, long long M, int N,
-                 int K, int act, void* stream) {
+                 int K, int act, int pairs_ok, void* stream) {
   static const bool enabled = [] { const char* e = getenv("LCE_B200_PW_TF32"); return !(e && e[0] == '0'); }();
   EncodeTiledFn enc = tensor_map_encoder();
   if (!enabled || enc == nullptr) return -1;
   if ((reinterpret_cast<uintptr_t>(in) | reinterpret_cast<uintptr_t>(filter) | reinterpret_cast<uintptr_t>(out) |
        reinterpret_cast<uintptr_t>(bias) | reinterpret_cast<uintptr_t>(packed)) & 15)
     return -1;
-  const bool pairs = K == 16 && N == 64 && (M & 1) == 0;
-  if (!pairs && ((K & 31) != 0 || (N & 127) != 0 || K > 4096)) return -1;
+  // Which kernel runs must not depend on the batch (an image's result must not change with its
+  // batch mates): eligibility looks at the layer's shape only; `pairs_ok` = even pixels per image.
+  const bool pairs = K == 16 && N == 64 && pairs_ok && (M & 1) == 0;
+  // N: whole 128-column tiles, or (no packed output) any multiple of 4 -- TMA zero-fills the filter
+  // rows past N and clips the stores (FULLY_CONNECTED's 1000 logits)
+  if (!pairs && ((K & 31) != 0 || K > 4096 || (N & 3) != 0 || ((N & 127) != 0 && packed != nullptr))) return -1;
   namespace P = lce::pw;
   P::PwParams p{};
   p.M = pairs ? M / 2 : M;
   p.N = pairs ? 128 : N;
   p.KB = pairs ? 1 : K / 32;
-  p.n_tiles = p.N / 128;
+  p.n_tiles = (p.N + 127) / 128;
   const long long m_tiles = (p.M + 127) / 128;
-  if (m_tiles * p.n_tiles < 32 || m_tiles > (1 << 22)) return -1;   // a handful of tiles: the small-M GEMM
+  if (m_tiles > (1 << 22)) return -1;
   p.m_tiles = static_cast<int>(m_tiles);
   p.act = act;
   p.pairs = pairs ? 1 : 0;
@@ -638,7 +642,7 @@ int stem7_tf32_conv(const float* in, const float* filter, const float* bias, flo
   P::Stem7Params p{};
   p.M = static_cast<long long>(B) * OH * OW;
   const long long m_tiles = (p.M + 127) / 128;
-  if (m_tiles < 32 || m_tiles > (1 << 23)) return -1;
+  if (m_tiles > (1 << 23)) return -1;
   p.H = H; p.W = W; p.OH = OH; p.OW = OW; p.ph = ph; p.pw = pw;
   p.m_tiles = static_cast<int>(m_tiles);
   p.act = act;

@@ -20,7 +20,7 @@ int fail(const char* fmt, ...);       // lce_b200.cu
 int launch_check(const char* what);   // lce_b200.cu
 // tcgen05 kind::tf32 pointwise convolution (lce_b200_pw.cuh): 0 launched, -1 not eligible
 int pw_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int32_t* packed, long long M, int N,
-                 int K, int act, void* stream);
+                 int K, int act, int pairs_ok, void* stream);
 // tcgen05 kind::tf32 7x7 / stride 2 / 3 -> 64 convolution (Bi-RealNet's stem): 0 launched, -1 not eligible
 int stem7_tf32_conv(const float* in, const float* filter, const float* bias, float* out, int B, int H, int W, int OH, int OW,
                     int ph, int pw, int act, void* stream);
@@ -1397,7 +1397,8 @@ static int conv2d_impl(const lce_f32_conv_desc* d, const float* in, const float*
   // 1x1 stride-1 convolutions are plain GEMMs over the pixels: tensor cores first
   if (g.KH == 1 && g.KW == 1 && g.sh == 1 && g.sw == 1) {
     int32_t* pk = (packed && (g.Cout & 31) == 0) ? packed : nullptr;
-    const int rc = lce_b200_internal::pw_tf32_conv(in, filter, bias, out, pk, M, g.Cout, K, g.act, stream);
+    const int rc = lce_b200_internal::pw_tf32_conv(in, filter, bias, out, pk, M, g.Cout, K, g.act,
+                                                   ((static_cast<long long>(g.OH) * g.OW) & 1) == 0, stream);
     if (rc >= 0) {
       if (rc == 0 && pk) *packed_done = true;
       return rc;

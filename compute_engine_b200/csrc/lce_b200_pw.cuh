@@ -280,7 +280,7 @@ pw_tf32_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__
 #pragma unroll
       for (int k = 0; k < 8; ++k) {
         float4 bi = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (p.bias) bi = __ldg(reinterpret_cast<const float4*>(p.bias + ((n0 + 4 * k) & p.bias_mask)));
+        if (p.bias && n0 + 4 * k < p.N) bi = __ldg(reinterpret_cast<const float4*>(p.bias + ((n0 + 4 * k) & p.bias_mask)));
         float y0 = __fadd_rn(__uint_as_float(v[4 * k]), bi.x), y1 = __fadd_rn(__uint_as_float(v[4 * k + 1]), bi.y);
         float y2 = __fadd_rn(__uint_as_float(v[4 * k + 2]), bi.z), y3 = __fadd_rn(__uint_as_float(v[4 * k + 3]), bi.w);
         if (p.act == LCE_ACT_RELU) {

@@ -114,6 +114,8 @@ def test_fused_stem_refuses_other_shapes():
     (9001, 128, 256, 1, True),         # weight ring, two column tiles
     (4999, 256, 512, 3, True),
     (8192, 96, 128, 2, False),
+    (256, 512, 1000, 0, False),        # FULLY_CONNECTED's logits: ragged last column tile, two row tiles
+    (1500, 64, 200, 1, False),
 ])
 def test_tf32_pointwise_conv_matches_fp64_product(M, K, N, act, with_packed):
     torch, lib = _env()
