@@ -397,9 +397,10 @@ TfLiteStatus MeanPrepare(TfLiteContext* c, TfLiteNode* n) {
 }
 TfLiteStatus MeanInvoke(TfLiteContext* c, TfLiteNode* n) {
   const TfLiteTensor* in = T(c, n->inputs, 0);
-  B_CAPI(c, lce_b200_f32_mean_hw(in->data.f, T(c, n->outputs, 0)->data.f, in->dims->data[0],
-                                 in->dims->data[1], in->dims->data[2], in->dims->data[3],
-                                 lce_b200_get_stream()));
+  // P(n).activation: a RELU folded in front of the mean by Graph::FuseFloatGlue (0 = none)
+  B_CAPI(c, lce_b200_f32_mean_hw_act(in->data.f, T(c, n->outputs, 0)->data.f, in->dims->data[0],
+                                     in->dims->data[1], in->dims->data[2], in->dims->data[3],
+                                     P(n).activation, lce_b200_get_stream()));
   return kTfLiteOk;
 }
 

@@ -533,6 +533,36 @@ int Graph::FuseFloatGlue() {
   // in registers and emits the sign words for free; other shapes pack with the stand-alone kernel
   const char* cq_env = getenv("LCE_B200_FUSE_CONV_QUANT");
   if (!(cq_env && cq_env[0] == '0')) removed += FuseConvQuantize();
+  // RELU -> MEAN (the model heads): the mean applies the activation as it reads
+  for (size_t i = 0; i < nodes_.size(); ++i) {
+    NodeRecord& relu = *nodes_[i];
+    if (relu.name != "builtin:19" || relu.initialized || relu.node.inputs->size != 1 || relu.node.outputs->size != 1)
+      continue;
+    const int y = relu.node.outputs->data[0];
+    if (std::find(outputs_.begin(), outputs_.end(), y) != outputs_.end()) continue;
+    size_t mi = nodes_.size();
+    int n_cons = 0;
+    for (size_t k = 0; k < nodes_.size(); ++k)
+      for (int q = 0; q < nodes_[k]->node.inputs->size; ++q)
+        if (nodes_[k]->node.inputs->data[q] == y) { ++n_cons; mi = k; }
+    if (n_cons != 1 || mi <= i) continue;
+    NodeRecord& mean = *nodes_[mi];
+    if (mean.name != "builtin:40" || mean.initialized || mean.node.inputs->data[0] != y ||
+        mean.builtin_blob.size() < sizeof(BuiltinParams))
+      continue;
+    reinterpret_cast<BuiltinParams*>(mean.builtin_blob.data())->activation = 1;   // kTfLiteActRelu
+    mean.node.builtin_data = mean.builtin_blob.data();
+    mean.node.inputs->data[0] = relu.node.inputs->data[0];
+    mean.name = "RELU+MEAN";
+    LceB200IntArrayFree(relu.node.inputs);
+    LceB200IntArrayFree(relu.node.outputs);
+    LceB200IntArrayFree(relu.node.temporaries);
+    LceB200IntArrayFree(relu.node.intermediates);
+    nodes_.erase(nodes_.begin() + i);
+    ++removed;
+    allocated_ = false;
+    break;
+  }
   for (size_t i = 0; i < nodes_.size(); ++i) {
     NodeRecord& pool = *nodes_[i];
     if (pool.name != "builtin:17" || pool.initialized ||

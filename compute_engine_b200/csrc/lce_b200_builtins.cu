@@ -956,34 +956,69 @@ __global__ void __launch_bounds__(256) eltwise_kernel(const float* __restrict__ 
 // mean over H*W: one thread per (b, c), c fastest => coalesced rows.
 __global__ void __launch_bounds__(256) mean_hw_kernel(const float* __restrict__ in,
                                                       float* __restrict__ out, int B, int HW,
-                                                      int C) {
+                                                      int C, int pre_act) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int b = i / C, c = i - b * C;
   const float* p = in + static_cast<size_t>(b) * HW * C + c;
   float s = 0.0f;
-  for (int k = 0; k < HW; ++k) s += p[static_cast<size_t>(k) * C];
+  for (int k = 0; k < HW; ++k) s += apply_act(p[static_cast<size_t>(k) * C], pre_act);
   out[i] = s / static_cast<float>(HW);
 }
 
-// softmax: one warp per row.
-__global__ void __launch_bounds__(256) softmax_kernel(const float* __restrict__ in,
-                                                      float* __restrict__ out, long long rows,
-                                                      int cols, float beta) {
-  const long long row = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (row >= rows) return;
-  const float* x = in + row * cols;
+// softmax: one CTA of 128 threads per row (a warp per row left 256 rows on 32 CTAs); the row
+// lives in registers between the three passes (<= 8 elements per thread, else re-read).
+__global__ void __launch_bounds__(128) softmax_kernel(const float* __restrict__ in,
+                                                      float* __restrict__ out, int cols, float beta) {
+  __shared__ float red[4];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float* x = in + static_cast<long long>(blockIdx.x) * cols;
+  float* y = out + static_cast<long long>(blockIdx.x) * cols;
+  constexpr int kR = 8;
+  const bool in_regs = cols <= kR * 128;
+  float v[kR];
   float mx = -FLT_MAX;
-  for (int c = lane; c < cols; c += 32) mx = fmaxf(mx, x[c]);
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+      const int c = tid + j * 128;
+      v[j] = c < cols ? x[c] : -FLT_MAX;
+      mx = fmaxf(mx, v[j]);
+    }
+  } else {
+    for (int c = tid; c < cols; c += 128) mx = fmaxf(mx, x[c]);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+  if (lane == 0) red[warp] = mx;
+  __syncthreads();
+  mx = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
   float sum = 0.0f;
-  for (int c = lane; c < cols; c += 32) sum += expf((x[c] - mx) * beta);
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+      const int c = tid + j * 128;
+      v[j] = c < cols ? expf((v[j] - mx) * beta) : 0.0f;
+      sum += v[j];
+    }
+  } else {
+    for (int c = tid; c < cols; c += 128) sum += expf((x[c] - mx) * beta);
+  }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-  float* y = out + row * cols;
-  for (int c = lane; c < cols; c += 32) y[c] = expf((x[c] - mx) * beta) / sum;
+  if (lane == 0) red[warp] = sum;
+  __syncthreads();
+  sum = (red[0] + red[1]) + (red[2] + red[3]);
+  if (in_regs) {
+#pragma unroll
+    for (int j = 0; j < kR; ++j) {
+      const int c = tid + j * 128;
+      if (c < cols) y[c] = v[j] / sum;
+    }
+  } else {
+    for (int c = tid; c < cols; c += 128) y[c] = expf((x[c] - mx) * beta) / sum;
+  }
 }
 
 // constant pad of a 4-D tensor of 32-bit elements (float32, or bitpacked int32 words).
@@ -1692,20 +1727,24 @@ int lce_b200_f32_activation(const float* in, float* out, int64_t n, int act, voi
   return launch_check("eltwise_kernel<act>");
 }
 
-int lce_b200_f32_mean_hw(const float* in, float* out, int batch, int h, int w, int c,
-                         void* stream) {
+int lce_b200_f32_mean_hw_act(const float* in, float* out, int batch, int h, int w, int c, int pre_activation,
+                             void* stream) {
   if (batch <= 0 || c <= 0) return 0;
   if (h * w <= 0) return fail("mean: empty spatial extent");
-  mean_hw_kernel<<<(batch * c + 255) / 256, 256, 0, as_stream(stream)>>>(in, out, batch, h * w, c);
+  mean_hw_kernel<<<(batch * c + 255) / 256, 256, 0, as_stream(stream)>>>(in, out, batch, h * w, c, pre_activation);
   return launch_check("mean_hw_kernel");
+}
+
+int lce_b200_f32_mean_hw(const float* in, float* out, int batch, int h, int w, int c,
+                         void* stream) {
+  return lce_b200_f32_mean_hw_act(in, out, batch, h, w, c, LCE_ACT_NONE, stream);
 }
 
 int lce_b200_f32_softmax(const float* in, float* out, int64_t rows, int cols, float beta,
                          void* stream) {
   if (rows <= 0 || cols <= 0) return 0;
-  const long long threads = rows * 32;
-  softmax_kernel<<<static_cast<unsigned>((threads + 255) / 256), 256, 0, as_stream(stream)>>>(
-      in, out, rows, cols, beta);
+  if (rows > 0x7fffffffLL) return fail("softmax: too many rows");
+  softmax_kernel<<<static_cast<unsigned>(rows), 128, 0, as_stream(stream)>>>(in, out, cols, beta);
   return launch_check("softmax_kernel");
 }
 

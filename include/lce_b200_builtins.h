@@ -84,6 +84,10 @@ int lce_b200_f32_activation(const float* in_dev, float* out_dev, int64_t n, int 
 /* mean over H and W: [B,H,W,C] -> [B,C] */
 int lce_b200_f32_mean_hw(const float* in_dev, float* out_dev, int batch, int h, int w, int c,
                          void* stream);
+/* the same with an activation applied to every element first: RELU -> MEAN of the model heads in one
+ * pass (mean(act(x)), the same summation order as the two ops) */
+int lce_b200_f32_mean_hw_act(const float* in_dev, float* out_dev, int batch, int h, int w, int c,
+                             int pre_activation, void* stream);
 /* softmax over the last dim: exp(beta*(x - max)) / sum */
 int lce_b200_f32_softmax(const float* in_dev, float* out_dev, int64_t rows, int cols, float beta,
                          void* stream);

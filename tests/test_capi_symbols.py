@@ -80,6 +80,6 @@ def test_no_cpu_fallback_without_device(lib):
 
 def test_builtin_kernels_header_symbols_are_exported(lib):
     names = declared_symbols("lce_b200_builtins.h")
-    assert len(names) == 16
+    assert len(names) == 17
     for n in names:
         assert hasattr(lib, n), f"{n} declared in include/lce_b200_builtins.h but not exported"

@@ -351,12 +351,13 @@ def test_residual_block_fusion_rewrites_the_graph():
     assert g.fuse_residual_blocks() == 0               # idempotent
     # float glue: the stem's conv 3x3 s2 -> depthwise 3x3 s2 pair (1 node removed), the four
     # CONV_2D -> LceQuantize pairs (stem pointwise + three transitions) and the three
-    # (max-pool 2x2 s1 -> blur depthwise 3x3 s2) pairs of the transitions
-    assert g.fuse_float_glue() == 1 + 4 + 3 and g.num_nodes() == 28
+    # (max-pool 2x2 s1 -> blur depthwise 3x3 s2) pairs of the transitions, and the head's RELU -> MEAN
+    assert g.fuse_float_glue() == 1 + 4 + 3 + 1 and g.num_nodes() == 27
     names = [g.node_name(i) for i in range(g.num_nodes())]
     assert names.count("MAX_POOL_2D+DEPTHWISE_CONV_2D") == 3 and "builtin:17" not in names
     assert names[0] == "CONV_2D+DEPTHWISE_CONV_2D" and "builtin:4" not in names
     assert names.count("CONV_2D+LceQuantize") == 4 and "LceQuantize" not in names
+    assert names.count("RELU+MEAN") == 1 and "builtin:19" not in names
     assert g.fuse_float_glue() == 0                    # idempotent
     g.close()
 
@@ -368,14 +369,14 @@ def test_fusion_switches_and_dequantize_folding(monkeypatch):
     blob = zoo.quicknet(batch=1, image=64, seed=3, input_type="int8")
     g = H.HostGraph.from_tflite(blob, device_arena=True)
     assert g.num_nodes() == 65
-    assert g.fuse_all() == 28 + 2 + 4 + 3 and g.num_nodes() == 28
+    assert g.fuse_all() == 28 + 2 + 4 + 3 + 1 and g.num_nodes() == 27
     names = [g.node_name(i) for i in range(g.num_nodes())]
     assert names[0] == "DEQUANTIZE+CONV_2D+DEPTHWISE_CONV_2D" and "builtin:6" not in names
     g.close()
     monkeypatch.setenv("LCE_B200_FUSE_STEM", "0")
     monkeypatch.setenv("LCE_B200_FUSE_CONV_QUANT", "0")
     g = H.HostGraph.from_tflite(blob, device_arena=True)
-    assert g.fuse_all() == 28 + 3 and g.num_nodes() == 34
+    assert g.fuse_all() == 28 + 3 + 1 and g.num_nodes() == 33
     names = [g.node_name(i) for i in range(g.num_nodes())]
     assert names[0] == "builtin:6" and names.count("builtin:4") == 1 and names.count("LceQuantize") == 4
     g.close()
@@ -396,7 +397,7 @@ def test_gpu_fused_graph_is_bit_identical_to_unfused(family, image, input_type):
         g = H.HostGraph.from_tflite(blob, device_arena=True)
         if fuse:
             assert g.fuse_residual_blocks() > 0
-            want = 0 if family != "quicknet" else (1 + 4 + 3 + (1 if input_type == "int8" else 0))
+            want = 0 if family != "quicknet" else (1 + 4 + 3 + 1 + (1 if input_type == "int8" else 0))
             assert g.fuse_float_glue() == want
         g.resize_input(g.inputs()[0], x.shape)
         g.allocate_tensors()
