@@ -46,7 +46,11 @@ namespace tc {
 #define LCE_TC_PROF 0   // 1: per-role cycle counters (build with -DLCE_TC_PROF=1, run with LCE_B200_TC_PROF=1)
 #endif
 constexpr int kBM = 128;
-constexpr int kThreads = 640;
+#ifndef LCE_TC_EXP_GROUPS
+#define LCE_TC_EXP_GROUPS 2   // expander warps per TMEM lane quarter (they take the A stages in turn)
+#endif
+constexpr int kExpGroups = LCE_TC_EXP_GROUPS;
+constexpr int kThreads = (4 * kExpGroups + 8 + 4) * 32;
 constexpr int kWS = 8;            // K words per stage
 constexpr int kNA = 4;            // A stages in TMEM, 64 columns each
 constexpr int kNR = 2;            // activation-halo stages
@@ -56,8 +60,9 @@ constexpr int kSlotBytes = kBM * 128;  // 128 rows x 32 columns x 4 B
 // Warp ids. The SM's schedulers favour the HIGHER warp id among eligible warps (measured: a
 // single-lane role at warp id 1 starved behind the busy expander / epilogue warps of its scheduler
 // and the tensor pipe idled half the time), so the latency-critical single-lane roles sit on top.
-constexpr int kFirstExpWarp = 0, kNumExpWarps = 8, kFirstEpiWarp = 8, kNumEpiWarps = 8;
-constexpr int kWarpActProd = 16, kWarpResProd = 17, kWarpWeightProd = 18, kWarpMma = 19;
+constexpr int kFirstExpWarp = 0, kNumExpWarps = 4 * kExpGroups, kFirstEpiWarp = kNumExpWarps, kNumEpiWarps = 8;
+constexpr int kWarpActProd = kFirstEpiWarp + 8, kWarpResProd = kWarpActProd + 1, kWarpWeightProd = kWarpActProd + 2,
+              kWarpMma = kWarpActProd + 3;
 constexpr int kTabBytes = 4 * 128 * 4 * 2;   // {mul, bias, wpop2, thr} x 128 channels, double-buffered
 constexpr int kBarBytes = 1024;
 
@@ -653,7 +658,7 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
         const uint32_t* raw = reinterpret_cast<const uint32_t*>(smem + p.off_raw + rs * p.raw_stage_bytes);
         mbar_wait_prof(&raw_full[rs], (cntR / kNR) & 1, 7, prof, pw[1]);
         for (int st = 0; st < nst; ++st, ++cntA) {
-          if ((cntA & 1) != static_cast<uint32_t>(group)) continue;
+          if ((cntA % kExpGroups) != static_cast<uint32_t>(group)) continue;
           const int as = cntA % kNA;
           uint32_t v[32];
           const long long tb0 = prof ? clock64() : 0;

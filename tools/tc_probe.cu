@@ -260,6 +260,101 @@ __global__ void __launch_bounds__(128) probe_rate2(int N, int iters, long long* 
   if (warp == 0) tmem_dealloc(tb, 512);
 }
 
+
+// ------------------------------------------------------------------ T8: MMA rate under TMEM / shared-memory traffic
+// The real kernels never reach T5's N/2 cycles per MMA (100-150 measured). Which neighbour slows
+// the tensor pipe down? One thread issues back-to-back TS MMAs (N = 128, two accumulators in
+// turn) while 8 other warps keep doing, until told to stop:
+//   bit 0: tcgen05.st x32 into TMEM columns the MMAs do not touch (what the expanders do)
+//   bit 1: tcgen05.ld x32 of other TMEM columns                    (what the epilogue does)
+//   bit 2: 128-bit shared-memory stores + loads                     (staging traffic)
+//   bit 3: a dense integer ALU stream                                (expander / epilogue arithmetic)
+// `real` = 1: the issuing thread derives every descriptor from loop-carried values like the kernels do.
+__global__ void __launch_bounds__(288) probe_contend(int mode, int iters, long long* cycles, int real) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  __shared__ volatile int stop;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < (128 + 256) * 128 / 16; i += 288) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x01010101u, 0x01ff01ffu, 0, 0x02020202u);
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); stop = 0; }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  if (warp < 4) {
+    uint32_t v[8] = {0x01010101u, 0, 0x01000100u, 0, 1, 2, 3, 4};
+    for (int c = 0; c < 64; c += 8) tmem_st8(tb + 256 + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  long long t0 = 0;
+  if (warp == 8) {
+    tc_fence_after();
+    const uint32_t idesc = make_idesc_i8(128, 128, 1, 1);
+    const uint32_t Bs = smem_u32(smem + 128 * 128);
+    const uint64_t bd0 = make_sdesc(Bs, 128, 1024, 0);
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    t0 = clock64();
+    if (pred) {
+      if (!real) {
+        for (int it = 0; it < iters; it += 16) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) mma_i8_ts(tb + (j & 1) * 128, tb + 256 + (j & 7) * 8, bd0 + (j & 3) * 16, idesc, 1);
+        }
+      } else {
+        uint32_t as = real - 1, d = 0;          // opaque to the compiler: stage / accumulator indices
+        for (int it = 0; it < iters; it += 8) {
+          const uint32_t a0 = tb + 256 + (as & 3) * 64 * 0 + (as & 1) * 0;
+          const uint64_t b0 = bd0 + static_cast<uint64_t>((as & 3) * 16);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mma_i8_ts(tb + (d & 1) * 128, a0 + j * 8, b0 + (j & 3) * 16, idesc, (it | j) != 0);
+          as += 1;
+          if ((as & 7) == 0) d ^= 1;
+        }
+      }
+      tc_commit(&bar);
+    }
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (lane == 0) { cycles[blockIdx.x] = clock64() - t0; stop = 1; }
+  } else {
+    // warps 0-7: lane quarter = warp & 3; columns 320..511 are free for them
+    const uint32_t tq = tb + (static_cast<uint32_t>((warp & 3) * 32) << 16);
+    uint32_t v[8] = {1, 2, 3, 4, 5, 6, 7, 8};
+    uint4* sp = reinterpret_cast<uint4*>(smem + (128 + 256) * 128) + tid;   // 8 KB scratch behind the operands
+    uint32_t acc = 0;
+    while (!stop) {
+      if (mode & 1) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) tmem_st8(tq + 320 + (warp >> 2) * 32 + c, v);
+        tmem_st_wait();
+      }
+      if (mode & 2) {
+#pragma unroll
+        for (int c = 0; c < 32; c += 8) { uint32_t r[8]; tmem_ld8(tq + 384 + (warp >> 2) * 32 + c, r); acc += r[0]; }
+      }
+      if (mode & 4) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { sp[k * 256] = make_uint4(acc, k, 0, 0); acc += sp[((k + 1) & 7) * 256].x; }
+      }
+      if (mode & 8) {
+#pragma unroll
+        for (int k = 0; k < 64; ++k) acc = acc * 0x9E3779B1u + (acc >> 7) + k;
+      }
+      if (mode == 0) __nanosleep(200);
+    }
+    if (acc == 0x12345678u) cycles[blockIdx.x] = 0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
 // ------------------------------------------------------------------ T6: per-stage overhead of the issuing thread
 // One "stage" = [optional: two try_waits on already-completed mbarriers] + fence + elect + 8 MMAs
 // with descriptors derived from loop-carried values (as the real kernel does) + [optional: two
@@ -684,6 +779,26 @@ int main() {
           printf("  N=%3d waits=%d commits=%d: %.0f cycles/stage (tensor %d)\n", N, w, c, static_cast<double>(cy[0]) / stages, 4 * N);
         }
     cudaFree(dc);
+  }
+  printf("T8: cycles per TS MMA (N = 128) while 8 other warps generate traffic\n");
+  {
+    CK(cudaFuncSetAttribute(probe_contend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * sizeof(long long)));
+    const char* names[8] = {"idle neighbours", "tcgen05.st", "tcgen05.ld", "tcgen05.st + ld", "shared ld/st", "st + shared", "ld + shared", "st + ld + shared"};
+    for (int real = 0; real < 2; ++real)
+      for (int mode : {0, 1, 2, 3, 4, 7, 8, 15}) {
+        const int iters = 4096;
+        probe_contend<<<148, 288, (128 + 256) * 128 + 9 * 1024 * 4>>>(mode, 64, dc, real);
+        CK(cudaDeviceSynchronize());
+        probe_contend<<<148, 288, (128 + 256) * 128 + 9 * 1024 * 4>>>(mode, iters, dc, real);
+        CK(cudaDeviceSynchronize());
+        long long h[148];
+        CK(cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost));
+        printf("  %s %-18s%s %.1f cycles/MMA (SM0), %.0f MAC/clk/SM\n", real ? "runtime descriptors," : "constant descriptors,",
+               names[mode & 7], (mode & 8) ? " + ALU stream" : "", static_cast<double>(h[0]) / iters, 128.0 * 128 * 32 * iters / h[0]);
+      }
+    CK(cudaFree(dc));
   }
   printf("T7: kind::tf32, TMA SWIZZLE_128B operands\n");
   {
