@@ -270,7 +270,7 @@ __global__ void __launch_bounds__(128) probe_rate2(int N, int iters, long long* 
 //   bit 2: 128-bit shared-memory stores + loads                     (staging traffic)
 //   bit 3: a dense integer ALU stream                                (expander / epilogue arithmetic)
 // `real` = 1: the issuing thread derives every descriptor from loop-carried values like the kernels do.
-__global__ void __launch_bounds__(288) probe_contend(int mode, int iters, long long* cycles, int real) {
+__global__ void __launch_bounds__(288) probe_contend(int mode, int iters, long long* cycles, int real, int no_mma = 0) {
   extern __shared__ __align__(1024) unsigned char smem[];
   __shared__ __align__(8) uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -300,7 +300,10 @@ __global__ void __launch_bounds__(288) probe_contend(int mode, int iters, long l
     uint32_t pred;
     asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
     t0 = clock64();
-    if (pred) {
+    if (no_mma) {                       // same duration, tensor pipe idle: the neighbours' baseline
+      while (clock64() - t0 < 64LL * iters) {}
+      if (lane == 0) { cycles[blockIdx.x] = clock64() - t0; stop = 1; }
+    } else if (pred) {
       if (!real) {
         for (int it = 0; it < iters; it += 16) {
 #pragma unroll
@@ -320,15 +323,19 @@ __global__ void __launch_bounds__(288) probe_contend(int mode, int iters, long l
       tc_commit(&bar);
     }
     __syncwarp();
-    mbar_wait(&bar, 0);
-    if (lane == 0) { cycles[blockIdx.x] = clock64() - t0; stop = 1; }
+    if (!no_mma) {
+      mbar_wait(&bar, 0);
+      if (lane == 0) { cycles[blockIdx.x] = clock64() - t0; stop = 1; }
+    }
   } else {
     // warps 0-7: lane quarter = warp & 3; columns 320..511 are free for them
     const uint32_t tq = tb + (static_cast<uint32_t>((warp & 3) * 32) << 16);
     uint32_t v[8] = {1, 2, 3, 4, 5, 6, 7, 8};
     uint4* sp = reinterpret_cast<uint4*>(smem + (128 + 256) * 128) + tid;   // 8 KB scratch behind the operands
     uint32_t acc = 0;
+    long long loops = 0;
     while (!stop) {
+      ++loops;
       if (mode & 1) {
 #pragma unroll
         for (int c = 0; c < 32; c += 8) tmem_st8(tq + 320 + (warp >> 2) * 32 + c, v);
@@ -349,6 +356,7 @@ __global__ void __launch_bounds__(288) probe_contend(int mode, int iters, long l
       if (mode == 0) __nanosleep(200);
     }
     if (acc == 0x12345678u) cycles[blockIdx.x] = 0;
+    if (tid == 0) cycles[148 + blockIdx.x] = loops;
   }
   tc_fence_before();
   __syncthreads();
@@ -487,6 +495,62 @@ __global__ void __launch_bounds__(128) probe_tf32(const __grid_constant__ CUtens
     tmem_ld8(tb + (static_cast<uint32_t>(warp * 32) << 16) + c0, v);
     for (int j = 0; j < 8; ++j) D[tid * N + c0 + j] = __uint_as_float(v[j]);
   }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tb, 512);
+}
+
+
+// ------------------------------------------------------------------ T9: kind::tf32 issue interval
+// Back-to-back tf32 MMAs (M 128, N 128, K 8), A from shared memory (SS) or from TMEM (TS), two
+// accumulators in turn. Nominal: half the bf16 rate = 64 cycles.
+__device__ __forceinline__ void mma_tf32_ts_probe(uint32_t d, uint32_t a_tmem, uint64_t bd, uint32_t idesc, uint32_t acc) {
+  asm volatile("{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+               "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n}\n" ::"r"(d), "r"(a_tmem), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+}
+__global__ void __launch_bounds__(128) probe_tf32_rate(int ts, int N, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  __shared__ __align__(8) uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (128 + 256) * 128 / 16; i += 128) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0x3f800000u, 0x3f000000u, 0, 0x40000000u);
+  fence_proxy_async();
+  if (tid == 0) { mbar_init(&bar, 1); fence_barrier_init(); }
+  if (warp == 0) tmem_alloc(&tmem_base_s, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tb = tmem_base_s;
+  {
+    uint32_t v[8] = {0x3f800000u, 0, 0x3f000000u, 0, 0x40000000u, 0, 0, 0x3f800000u};
+    for (int c = 0; c < 64; c += 8) tmem_st8(tb + 256 + (static_cast<uint32_t>(warp * 32) << 16) + c, v);
+    tmem_st_wait();
+    tc_fence_before();
+  }
+  __syncthreads();
+  long long t0 = 0;
+  if (warp == 0) {
+    tc_fence_after();
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (static_cast<uint32_t>(N >> 3) << 17) | (8u << 24);
+    const uint64_t ad0 = make_sdesc(smem_u32(smem), 128, 1024, 0);
+    const uint64_t bd0 = make_sdesc(smem_u32(smem + 128 * 128), 128, 1024, 0);
+    uint32_t pred;
+    asm volatile("{\n.reg .pred P;\nelect.sync _|P, 0xffffffff;\nselp.u32 %0, 1, 0, P;\n}\n" : "=r"(pred));
+    t0 = clock64();
+    if (pred) {
+      for (int it = 0; it < iters; it += 16) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          if (ts) mma_tf32_ts_probe(tb + (j & 1) * N, tb + 256 + (j & 7) * 8, bd0 + (j & 3) * 16, idesc, 1);
+          else mma_tf32_ss(tb + (j & 1) * N, ad0 + (j & 3) * 16, bd0 + (j & 3) * 16, idesc, 1);
+        }
+      }
+      tc_commit(&bar);
+    }
+    __syncwarp();
+  }
+  mbar_wait(&bar, 0);
+  if (tid == 0) cycles[blockIdx.x] = clock64() - t0;
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tb, 512);
@@ -784,7 +848,7 @@ int main() {
   {
     CK(cudaFuncSetAttribute(probe_contend, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     long long* dc;
-    CK(cudaMalloc(&dc, 148 * sizeof(long long)));
+    CK(cudaMalloc(&dc, 2 * 148 * sizeof(long long)));
     const char* names[8] = {"idle neighbours", "tcgen05.st", "tcgen05.ld", "tcgen05.st + ld", "shared ld/st", "st + shared", "ld + shared", "st + ld + shared"};
     for (int real = 0; real < 2; ++real)
       for (int mode : {0, 1, 2, 3, 4, 7, 8, 15}) {
@@ -797,6 +861,44 @@ int main() {
         CK(cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost));
         printf("  %s %-18s%s %.1f cycles/MMA (SM0), %.0f MAC/clk/SM\n", real ? "runtime descriptors," : "constant descriptors,",
                names[mode & 7], (mode & 8) ? " + ALU stream" : "", static_cast<double>(h[0]) / iters, 128.0 * 128 * 32 * iters / h[0]);
+      }
+    CK(cudaFree(dc));
+  }
+  printf("T10: do running MMAs slow the neighbours' TMEM traffic? (warp 0: loops of 4 x tcgen05.st/ld x8 + wait)\n");
+  {
+    long long* dc;
+    CK(cudaMalloc(&dc, 2 * 148 * sizeof(long long)));
+    for (int mode : {1, 2, 4}) {
+      double rate[2];
+      for (int no_mma = 0; no_mma < 2; ++no_mma) {
+        const int iters = 8192;
+        probe_contend<<<148, 288, (128 + 256) * 128 + 9 * 1024 * 4>>>(mode, iters, dc, 0, no_mma);
+        CK(cudaDeviceSynchronize());
+        long long h[296];
+        CK(cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost));
+        rate[no_mma] = static_cast<double>(h[0]) / h[148];
+      }
+      printf("  %-12s %.0f cycles per loop while MMAs run back to back, %.0f with the tensor pipe idle\n",
+             mode == 1 ? "tcgen05.st" : mode == 2 ? "tcgen05.ld" : "shared ld/st", rate[0], rate[1]);
+    }
+    CK(cudaFree(dc));
+  }
+  printf("T9: kind::tf32 issue interval (M 128, K 8)\n");
+  {
+    CK(cudaFuncSetAttribute(probe_tf32_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    long long* dc;
+    CK(cudaMalloc(&dc, 148 * sizeof(long long)));
+    for (int ts = 0; ts < 2; ++ts)
+      for (int N : {64, 128, 256}) {
+        const int iters = 4096;
+        probe_tf32_rate<<<148, 128, (128 + 256) * 128>>>(ts, N, 64, dc);
+        CK(cudaDeviceSynchronize());
+        probe_tf32_rate<<<148, 128, (128 + 256) * 128>>>(ts, N, iters, dc);
+        CK(cudaDeviceSynchronize());
+        long long h[148];
+        CK(cudaMemcpy(h, dc, sizeof(h), cudaMemcpyDeviceToHost));
+        printf("  %s N=%3d: %.1f cycles/MMA (SM0), %.0f MAC/clk/SM\n", ts ? "TS" : "SS", N, static_cast<double>(h[0]) / iters,
+               128.0 * N * 8 * iters / h[0]);
       }
     CK(cudaFree(dc));
   }
