@@ -452,10 +452,6 @@ int tc_launch(GemmCore& c, const lce::ConvKParams& p, cudaStream_t s) {
   t.off_bar = t.off_tab + T::kTabBytes;
   const size_t smem = static_cast<size_t>(t.off_bar) + T::kBarBytes;
   t.clamp_min = p.clamp_min; t.clamp_max = p.clamp_max;
-  {
-    static const bool off = [] { const char* e = getenv("LCE_B200_TC_FLOAT_EPI"); return e && e[0] == '0'; }();   // A/B
-    t.float_epilogue = (!off && static_cast<long long>(t.Kw_total) * 32 * 8 < (1 << 24)) ? 1 : 0;
-  }
   t.has_res = has_res ? 1 : 0; t.residual_act = p.residual_act;
   t.cw_out = p.cw_out; t.zp_half = p.zp_half; t.ldc = c.tc_ldc;
   t.wt = c.tc_wt; t.mul = p.mul; t.bias = p.bias; t.wpop2 = c.tc_wpop2; t.thr = p.thr;

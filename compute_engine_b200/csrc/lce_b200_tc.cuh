@@ -82,7 +82,6 @@ struct TcParams {
   int off_raw, off_slots, off_tab, off_bar;   // byte offsets in dynamic shared memory (weights at 0)
   int Kw_total;          // taps * Cw: K words per output channel
   int clamp_min, clamp_max;
-  int float_epilogue;      // 8 * K bits < 2^24: the float-domain epilogue is exact (epilogue_float_chunk_f)
   int has_res, residual_act, cw_out, zp_half, ldc;   // ldc: padded channel count of the tables
   int zp_float, cin_pg;  // zero padding as the optimised reference kernels do it (float correction)
   const uint8_t* wt;       // [n_tiles][stage][BN x (32 * words) B core-matrix image], stages dense
@@ -428,64 +427,6 @@ __device__ __forceinline__ uint32_t epilogue_float_chunk(const TcParams& p, cons
   }
   return bits;
 }
-// The same chunk computed in the FLOAT domain from the raw accumulators (no integer zero-padding
-// correction pending): x = acc8 / 4 + 2 popc(w) is formed as fma(float(acc8), 0.25, float(2 popc))
-// -- exact, every value is an integer below 2^24 (the launch checks 8 K < 2^24) -- the int32 clamp
-// becomes a float clamp with the same bounds (bounds beyond +-2^24 never bind; the host passes
-// which side can), and multiply / bias / shortcut run two channels per instruction (FMUL2 /
-// FADD2: separately rounded like the scalar ops). Same bits as epilogue_float_chunk, ~40 % fewer
-// instructions -- the first stages are issue-bound.
-template <bool RES, bool ACT, bool ZPF>
-__device__ __forceinline__ uint32_t epilogue_float_chunk_f(const TcParams& p, const uint32_t (&a8)[32], unsigned char* buf,
-                                                           int lane, const int* tab_cc, float act_lo, float act_hi,
-                                                           int zrow, int c0) {
-  uint32_t bits = 0;
-  const float cmin = static_cast<float>(p.clamp_min), cmax = static_cast<float>(p.clamp_max);
-  const bool need_lo = p.clamp_min > -(1 << 25), need_hi = p.clamp_max < (1 << 25);
-  const float2 quarter = make_float2(0.25f, 0.25f);
-#pragma unroll
-  for (int k = 0; k < 8; ++k) {
-    float4* cell = reinterpret_cast<float4*>(buf + ((k ^ (lane & 7)) << 4));
-    const float4 wp = reinterpret_cast<const float4*>(tab_cc + 384)[k];
-    const float4 mu = reinterpret_cast<const float4*>(tab_cc + 128)[k];
-    const float4 bi = reinterpret_cast<const float4*>(tab_cc + 256)[k];
-    float2 x0 = __ffma2_rn(make_float2(static_cast<float>(static_cast<int>(a8[4 * k])), static_cast<float>(static_cast<int>(a8[4 * k + 1]))),
-                           quarter, make_float2(wp.x, wp.y));
-    float2 x1 = __ffma2_rn(make_float2(static_cast<float>(static_cast<int>(a8[4 * k + 2])), static_cast<float>(static_cast<int>(a8[4 * k + 3]))),
-                           quarter, make_float2(wp.z, wp.w));
-    if (need_lo) { x0.x = fmaxf(x0.x, cmin); x0.y = fmaxf(x0.y, cmin); x1.x = fmaxf(x1.x, cmin); x1.y = fmaxf(x1.y, cmin); }
-    if (need_hi) { x0.x = fminf(x0.x, cmax); x0.y = fminf(x0.y, cmax); x1.x = fminf(x1.x, cmax); x1.y = fminf(x1.y, cmax); }
-    float2 y0 = __fadd2_rn(__fmul2_rn(x0, make_float2(mu.x, mu.y)), make_float2(bi.x, bi.y));
-    float2 y1 = __fadd2_rn(__fmul2_rn(x1, make_float2(mu.z, mu.w)), make_float2(bi.z, bi.w));
-    if (ZPF) {
-      const float4 cv = __ldg(reinterpret_cast<const float4*>(p.zpc_cache + static_cast<size_t>(max(zrow, 0)) * p.ldc + c0) + k);
-      if (zrow >= 0) {
-        y0 = __fadd2_rn(y0, make_float2(cv.x, cv.y));
-        y1 = __fadd2_rn(y1, make_float2(cv.z, cv.w));
-      }
-    }
-    if (RES) {
-      const float4 rv = *cell;
-      y0 = __fadd2_rn(y0, make_float2(rv.x, rv.y));
-      y1 = __fadd2_rn(y1, make_float2(rv.z, rv.w));
-      if (ACT) {
-        y0.x = fminf(fmaxf(y0.x, act_lo), act_hi); y0.y = fminf(fmaxf(y0.y, act_lo), act_hi);
-        y1.x = fminf(fmaxf(y1.x, act_lo), act_hi); y1.y = fminf(fmaxf(y1.y, act_lo), act_hi);
-      }
-    }
-    *cell = make_float4(y0.x, y0.y, y1.x, y1.y);
-    bits |= ((y0.x < 0.0f ? 1u : 0u) | (y0.y < 0.0f ? 2u : 0u) | (y1.x < 0.0f ? 4u : 0u) | (y1.y < 0.0f ? 8u : 0u)) << (4 * k);
-  }
-  return bits;
-}
-template <bool RES, bool ACT>
-__device__ __forceinline__ uint32_t epilogue_float_chunk_fzp(const TcParams& p, const uint32_t (&a8)[32], unsigned char* buf,
-                                                             int lane, const int* tab_cc, float act_lo, float act_hi,
-                                                             int zrow, int c0) {
-  if (__any_sync(0xffffffffu, zrow >= 0))
-    return epilogue_float_chunk_f<RES, ACT, true>(p, a8, buf, lane, tab_cc, act_lo, act_hi, zrow, c0);
-  return epilogue_float_chunk_f<RES, ACT, false>(p, a8, buf, lane, tab_cc, act_lo, act_hi, zrow, c0);
-}
 template <bool RES, bool ACT>
 __device__ __forceinline__ uint32_t epilogue_float_chunk_zp(const TcParams& p, const int (&x)[32], unsigned char* buf,
                                                             int lane, const int* tab_cc, float act_lo, float act_hi,
@@ -795,7 +736,6 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
           } else if (OUT != LCE_OUT_RAW_ACC) {
             tab[128 + etid] = __float_as_int(p.mul[c]);
             tab[256 + etid] = __float_as_int(p.bias[c]);
-            tab[384 + etid] = __float_as_int(static_cast<float>(p.wpop2[c]));   // for the float-domain epilogue
           }
         }
         named_bar_sync(1, kNumEpiWarps * 32);
@@ -828,11 +768,8 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
           if (lane == 0) mbar_arrive(&d_empty[ds]);
         }
         const int c0 = c_tile + cc * 32;
-        // float output with no integer correction pending (warp-uniform): the float-domain epilogue
-        const bool fast_f = OUT == LCE_OUT_FLOAT && p.float_epilogue && !__any_sync(0xffffffffu, oob != 0);
         // x = 2 * acc = (acc8 >> 2) + 2 * popc(w)   (acc8 is a multiple of 8)
         int x[32];
-        if (!fast_f) {
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const int4 wp = reinterpret_cast<const int4*>(tab + cc * 32)[k];
@@ -840,7 +777,6 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
           x[4 * k + 1] = (static_cast<int>(accu[4 * k + 1]) >> 2) + wp.y;
           x[4 * k + 2] = (static_cast<int>(accu[4 * k + 2]) >> 2) + wp.z;
           x[4 * k + 3] = (static_cast<int>(accu[4 * k + 3]) >> 2) + wp.w;
-        }
         }
         if (oob != 0) {
           for (unsigned long long mk = oob; mk != 0; mk &= mk - 1) {
@@ -882,11 +818,6 @@ bconv_tc_kernel(const __grid_constant__ CUtensorMap tm_in, const __grid_constant
             for (int k = 0; k < 8; ++k)
               *reinterpret_cast<uint4*>(buf + ((k ^ (lane & 7)) << 4)) =
                   make_uint4(x[4 * k] >> 1, x[4 * k + 1] >> 1, x[4 * k + 2] >> 1, x[4 * k + 3] >> 1);
-          } else if (fast_f) {
-            if (!res) bits = epilogue_float_chunk_fzp<false, false>(p, accu, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
-            else if (p.residual_act == LCE_ACT_NONE)
-              bits = epilogue_float_chunk_fzp<true, false>(p, accu, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
-            else bits = epilogue_float_chunk_fzp<true, true>(p, accu, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
           } else if (!res) {
             bits = epilogue_float_chunk_zp<false, false>(p, x, buf, lane, tab + cc * 32, act_lo, act_hi, zrow, c0);
           } else if (p.residual_act == LCE_ACT_NONE) {
