@@ -832,7 +832,10 @@ __global__ void __launch_bounds__(256) pool_v4_kernel(const float4* __restrict__
 // one output pixel x 4 channels; the 4x4 input window is loaded once (16 x LDG.128), the nine
 // pooled values are formed in registers and multiplied in the same (fy, fx) order as
 // depthwise_v4_kernel, so the result is bit-identical to the two-kernel sequence.
-__global__ void __launch_bounds__(256, 4) pool2_dw3_v4_kernel(const float4* __restrict__ in,
+#ifndef LCE_POOL_MINBLOCKS
+#define LCE_POOL_MINBLOCKS 4
+#endif
+__global__ void __launch_bounds__(256, LCE_POOL_MINBLOCKS) pool2_dw3_v4_kernel(const float4* __restrict__ in,
                                                               const float4* __restrict__ filter,
                                                               const float4* __restrict__ bias,
                                                               float4* __restrict__ out, int H, int W,
