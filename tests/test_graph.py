@@ -461,3 +461,52 @@ def test_gpu_pad_concat_graph_matches_reference():
     got = g.read(g.outputs()[0])
     g.close()
     assert got.shape == want[0].shape and np.array_equal(got, want[0])
+
+
+def test_float_glue_fusions_respect_their_preconditions():
+    """Pure host logic: RELU -> MEAN folds only when the RELU's output has no other reader; the stem
+    fusion needs CONSTANT filters (the kernel takes them by value) and a 3-channel 3x3/s2 conv."""
+    from compute_engine_b200.tflite_writer import TFLiteModel
+    rng = np.random.default_rng(0)
+    axes = np.array([1, 2], np.int32)
+
+    def head(relu_also_an_output):
+        m = TFLiteModel()
+        x = m.add_tensor("x", (2, 7, 7, 32))
+        r = m.add_tensor("r", (2, 7, 7, 32))
+        p = m.add_tensor("p", (2, 32))
+        ax = m.add_tensor("axes", None, np.int32, data=axes)
+        m.add_op("RELU", [x], [r])
+        m.add_op("MEAN", [r, ax], [p], keep_dims=False)
+        m.inputs, m.outputs = [x], ([p, r] if relu_also_an_output else [p])
+        return m.serialize()
+
+    g = H.HostGraph.from_tflite(head(False), device_arena=True)
+    assert g.fuse_float_glue() == 1 and [g.node_name(i) for i in range(g.num_nodes())] == ["RELU+MEAN"]
+    g.close()
+    g = H.HostGraph.from_tflite(head(True), device_arena=True)      # the RELU's output is also a graph output
+    assert g.fuse_float_glue() == 0 and g.num_nodes() == 2
+    g.close()
+
+    def stem(cin, const_filter):
+        m = TFLiteModel()
+        x = m.add_tensor("x", (1, 32, 32, cin))
+        w1d = (rng.standard_normal((16, 3, 3, cin)) * 0.2).astype(np.float32)
+        w1 = m.add_tensor("w1", None, np.float32, data=w1d) if const_filter else m.add_tensor("w1", (16, 3, 3, cin))
+        b1 = m.add_tensor("b1", None, np.float32, data=np.zeros(16, np.float32))
+        y = m.add_tensor("y", (1, 16, 16, 16))
+        w2 = m.add_tensor("w2", None, np.float32, data=(rng.standard_normal((1, 3, 3, 16)) * 0.3).astype(np.float32))
+        b2 = m.add_tensor("b2", None, np.float32, data=np.zeros(16, np.float32))
+        z = m.add_tensor("z", (1, 8, 8, 16))
+        m.add_op("CONV_2D", [x, w1, b1], [y], padding="SAME", stride=(2, 2), activation="RELU")
+        m.add_op("DEPTHWISE_CONV_2D", [y, w2, b2], [z], padding="SAME", stride=(2, 2), depth_multiplier=1)
+        m.inputs, m.outputs = ([x] if const_filter else [x, w1]), [z]
+        return m.serialize()
+
+    for cin, const_filter, fused in ((3, True, True), (4, True, False), (3, False, False)):
+        g = H.HostGraph.from_tflite(stem(cin, const_filter), device_arena=True)
+        removed = g.fuse_float_glue()
+        names = [g.node_name(i) for i in range(g.num_nodes())]
+        assert (removed == 1 and names == ["CONV_2D+DEPTHWISE_CONV_2D"]) if fused else (removed == 0 and len(names) == 2), \
+            (cin, const_filter, names)
+        g.close()
