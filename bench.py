@@ -542,11 +542,16 @@ def graph_workload(D, workload, B, input_type, steps, warmup, want_e2e=True, wan
                           f"{g.shape(ins[0])} -> {g.shape(outs[0])}", file=sys.stderr)
             conv_ms = conv_bytes = conv_words = 0
             n_conv = 0
+            glue_bytes = 0      # float / byte builtins: every operand read once, the result written once
             by_op = {}
             for i in range(g.num_nodes()):
                 name = g.node_name(i)
                 by_op[name] = by_op.get(name, 0.0) + node_ms[i]
                 if not name.startswith("LceBconv2d"):
+                    ins, outs = g.node_io(i)
+                    glue_bytes += sum(g.nbytes(t) for t in ins if t >= 0) + g.nbytes(outs[0])
+                    if "+LceQuantize" in name:
+                        glue_bytes += int(np.prod(g.shape(outs[0]))) // 8
                     continue
                 ins, outs = g.node_io(i)
                 conv_ms += node_ms[i]
@@ -557,7 +562,8 @@ def graph_workload(D, workload, B, input_type, steps, warmup, want_e2e=True, wan
                     conv_bytes += int(np.prod(g.shape(outs[0]))) // 8
                 conv_words += bconv_word_ops(g.shape(outs[0]), g.shape(ins[1]))
                 n_conv += 1
-            res.update({"conv_s_per_step": conv_ms * 1e-3 / steps, "conv_bytes": conv_bytes,
+            res.update({"step_alg_bytes": conv_bytes + glue_bytes,
+                        "conv_s_per_step": conv_ms * 1e-3 / steps, "conv_bytes": conv_bytes,
                         "conv_words": conv_words, "n_conv": n_conv * steps,
                         "conv_share": conv_ms / prof_ms if prof_ms else None,
                         "eager_ms_per_step": prof_ms / steps,
@@ -837,6 +843,13 @@ def main_b200(args):
                       "the graph's stream (events cannot sit inside a replayed CUDA graph)",
             "tensor": tensor_block(r["conv_words"], r["conv_s_per_step"], bf16_peak, sm_max)},
     }
+    if r.get("step_alg_bytes"):
+        floor_ms = r["step_alg_bytes"] / (hbm_peak * 1e9) * 1e3
+        line["step_roofline"] = {"alg_bytes_per_step": r["step_alg_bytes"], "hbm_ms": floor_ms,
+                                 "frac": floor_ms / (r["total_ms"] / K),
+                                 "note": "all kernels of one step: operands read once + results written once "
+                                         "(binary layers: SURVEY 8d bytes) at the measured HBM rate, against "
+                                         "ms_per_step"}
     if r.get("e2e_ms") is not None:
         line["e2e"] = {"value": B * D.world / (r["e2e_ms"] / K * 1e-3), "unit": "images/s",
                        "h2d_bytes_per_step": r["in_bytes"], "d2h_bytes_per_step": r["out_bytes"],
